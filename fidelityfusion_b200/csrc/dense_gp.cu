@@ -1,0 +1,484 @@
+// Host side of the dense GP path: workspace layout, the recursive potrf+trtri driver and the
+// C-ABI entry points declared in include/ffgp.h.  No allocation, no host synchronisation.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "../../include/ffgp.h"
+#include "dense_kernels.cuh"
+#include "gemm_dmma.cuh"
+
+namespace ffgp {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+#define FFGP_CUDA(x)                                                   \
+  do {                                                                 \
+    cudaError_t e__ = (x);                                             \
+    if (e__ != cudaSuccess) return fail(-100, "CUDA error: %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// ---------------------------------------------------------------------------------------------
+// GEMM dispatch: layout flags -> template instance; tile size by divisibility and machine fill
+// ---------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long long sA, const double* B, int ldb,
+                        long long sB, double* C, int ldc, long long sC, int M, int N, int K, double alpha, double beta,
+                        int lower_only, int kmode, int batch, cudaStream_t st) {
+  GemmParams p;
+  p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.sA = sA; p.sB = sB; p.sC = sC; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only; p.kmode = kmode;
+  p.heavy_first = 1;
+  bool big = (M % 128 == 0) && (N % 128 == 0);
+  if (big) {
+    const long long tm = M / 128, tn = N / 128;
+    const long long tiles = (lower_only ? tm * (tm + 1) / 2 : tm * tn) * batch;
+    if (tiles < (long long)num_sms()) big = false;     // 64x64 tiles: 4x the CTAs for the small levels
+  }
+  if (a_kmaj && b_kmaj) return launch_gemm<true, true>(p, batch, big, st);
+  if (a_kmaj && !b_kmaj) return launch_gemm<true, false>(p, batch, big, st);
+  if (!a_kmaj && b_kmaj) return launch_gemm<false, true>(p, batch, big, st);
+  return launch_gemm<false, false>(p, batch, big, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Workspace
+// ---------------------------------------------------------------------------------------------
+struct DenseWs {
+  int np, Dp, nsp, chunk, nblk, ngtile;
+  bool gemm_rhs;          // D > 8: right-hand sides go through the GEMM kernel
+  double *A, *L, *M;      // [chunk][np][np]
+  double *Gm, *alpha;     // [chunk][np][Dw]   (Dw = D when !gemm_rhs, else Dp)
+  double* Ypad;           // [chunk][np][Dp]   (gemm_rhs only)
+  double *rowsq;          // [chunk][np]
+  double *logdet_part;    // [chunk][nblk]
+  double *partial;        // [chunk][ngtile][d+1]
+  double *Kx, *V;         // [chunk][np][nsp]
+  double *Kxx;            // [chunk][nsp][nsp]
+  double *colsq;          // [chunk][nsp]
+  double *meanp;          // [chunk][nsp][Dp]
+  size_t bytes;
+};
+
+static const size_t WS_TARGET_BYTES = (size_t)6 << 30;   // per-chunk working set bound for big batches
+
+static DenseWs layout_ws(int n, int d, int D, int ns, int batch, char* base) {
+  DenseWs w;
+  w.np = round_up(std::max(n, 1), 128);
+  w.gemm_rhs = D > 8;
+  w.Dp = round_up(std::max(D, 1), 64);
+  w.nsp = ns > 0 ? round_up(ns, 64) : 0;
+  w.nblk = w.np / 128;
+  const int gt = w.np / GRAD_T;
+  w.ngtile = gt * (gt + 1) / 2;
+  const int Dw = w.gemm_rhs ? w.Dp : D;
+  auto per_item = [&]() {
+    size_t s = 0;
+    s += 3 * align256((size_t)w.np * w.np * 8);
+    s += 2 * align256((size_t)w.np * Dw * 8);
+    if (w.gemm_rhs) s += align256((size_t)w.np * w.Dp * 8);
+    s += align256((size_t)w.np * 8) + align256((size_t)w.nblk * 8) + align256((size_t)w.ngtile * (d + 1) * 8);
+    if (w.nsp) {
+      s += 2 * align256((size_t)w.np * w.nsp * 8) + align256((size_t)w.nsp * w.nsp * 8) + align256((size_t)w.nsp * 8);
+      s += align256((size_t)w.nsp * w.Dp * 8);
+    }
+    return s;
+  };
+  const size_t item = per_item();
+  long long chunk = (long long)(WS_TARGET_BYTES / item);
+  if (chunk < 1) chunk = 1;
+  w.chunk = (int)std::min<long long>(chunk, std::max(batch, 1));
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    char* ptr = base ? base + off : nullptr;
+    off += align256(nbytes) ;
+    return reinterpret_cast<double*>(ptr);
+  };
+  const size_t c = (size_t)w.chunk;
+  w.A = take(c * w.np * w.np * 8);
+  w.L = take(c * w.np * w.np * 8);
+  w.M = take(c * w.np * w.np * 8);
+  w.Gm = take(c * w.np * Dw * 8);
+  w.alpha = take(c * w.np * Dw * 8);
+  w.Ypad = w.gemm_rhs ? take(c * w.np * w.Dp * 8) : nullptr;
+  w.rowsq = take(c * w.np * 8);
+  w.logdet_part = take(c * w.nblk * 8);
+  w.partial = take(c * w.ngtile * (d + 1) * 8);
+  if (w.nsp) {
+    w.Kx = take(c * w.np * w.nsp * 8);
+    w.V = take(c * w.np * w.nsp * 8);
+    w.Kxx = take(c * w.nsp * w.nsp * 8);
+    w.colsq = take(c * w.nsp * 8);
+    w.meanp = take(c * w.nsp * w.Dp * 8);
+  } else {
+    w.Kx = w.V = w.Kxx = w.colsq = w.meanp = nullptr;
+  }
+  w.bytes = off + 256;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Recursive blocked factorisation:  (L, M = L^-1) of the block [off, off+n) of A.
+//   F(A11) ; L21 = A21 M11^T ; A22 -= L21 L21^T ; F(A22) ; T = M22 L21 (into the dead A21) ; M21 = -T M11
+// Every step above the 128x128 base is one DMMA GEMM launch over the whole batch; the triangular
+// operands only shorten the K range of a tile, never add a special kernel.
+// ---------------------------------------------------------------------------------------------
+struct FactorCtx {
+  double *A, *L, *M;
+  int ld;
+  long long sb;           // batch stride (elements)
+  int batch;
+  double* logdet_part; int nblk;
+  int* info;
+  cudaStream_t st;
+};
+
+static cudaError_t factor_rec(const FactorCtx& c, int off, int n) {
+  cudaError_t e;
+  const long long d0 = (long long)off * c.ld + off;
+  if (n == BASE_N) {
+    potrf_trtri_base_kernel<<<c.batch, 256, BASE_SMEM, c.st>>>(c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part,
+                                                               c.nblk, off / BASE_N, c.info, off);
+    return cudaGetLastError();
+  }
+  // split at a multiple of 128: top half gets the larger power-of-two-ish share
+  int h = ((n / BASE_N) + 1) / 2 * BASE_N;
+  const int m = n - h;
+  if ((e = factor_rec(c, off, h)) != cudaSuccess) return e;
+  const long long o21 = (long long)(off + h) * c.ld + off;
+  const long long o22 = (long long)(off + h) * c.ld + off + h;
+  // L21 = A21 * M11^T          (M11[j][p] = 0 for p > j)
+  if ((e = gemm(true, true, c.A + o21, c.ld, c.sb, c.M + d0, c.ld, c.sb, c.L + o21, c.ld, c.sb, m, h, h, 1.0, 0.0, 0,
+                K_LE_COL, c.batch, c.st)) != cudaSuccess) return e;
+  // A22 -= L21 L21^T           (lower tiles)
+  if ((e = gemm(true, true, c.L + o21, c.ld, c.sb, c.L + o21, c.ld, c.sb, c.A + o22, c.ld, c.sb, m, m, h, -1.0, 1.0, 1,
+                K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+  if ((e = factor_rec(c, off + h, m)) != cudaSuccess) return e;
+  // T = M22 * L21  -> A21      (M22[i][p] = 0 for p > i)
+  if ((e = gemm(true, false, c.M + o22, c.ld, c.sb, c.L + o21, c.ld, c.sb, c.A + o21, c.ld, c.sb, m, h, m, 1.0, 0.0, 0,
+                K_LE_ROW, c.batch, c.st)) != cudaSuccess) return e;
+  // M21 = -T * M11             (M11[p][j] = 0 for p < j)
+  if ((e = gemm(true, false, c.A + o21, c.ld, c.sb, c.M + d0, c.ld, c.sb, c.M + o21, c.ld, c.sb, m, h, h, -1.0, 0.0, 0,
+                K_GE_COL, c.batch, c.st)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+static bool g_attr_done = false;
+static cudaError_t ensure_attrs() {
+  if (g_attr_done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(potrf_trtri_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) return e;
+  g_attr_done = true;
+  return cudaSuccess;
+}
+
+static size_t grad_smem_bytes(int d) {
+  return (size_t)(2 * GRAD_T * (d + 1) + 2 * GRAD_T * 8 + 8 * (GRAD_DMAX + 1)) * sizeof(double);
+}
+
+struct DenseArgs {
+  const double *x, *y, *inv_ls, *amp, *diag_add, *sigma_add;
+  int n, d, D, batch, params_batched, diag_batched, clamp;
+};
+
+// Assemble Sigma (lower) into ws.A and factor it: ws.L, ws.M, logdet partials.  Chunk-local batch nb.
+static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int nb, int* info, cudaStream_t st) {
+  KernelMatrixParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.x1 = a.x ? a.x + (long long)b0 * a.n * a.d : nullptr;
+  kp.x2 = kp.x1;
+  kp.sx1 = kp.sx2 = (long long)a.n * a.d;
+  kp.w = a.inv_ls ? a.inv_ls + (a.params_batched ? (long long)b0 * a.d : 0) : nullptr;
+  kp.sw = a.params_batched ? a.d : 0;
+  kp.amp = a.amp ? a.amp + (a.params_batched ? b0 : 0) : nullptr;
+  kp.samp = a.params_batched ? 1 : 0;
+  kp.diag_add = a.diag_add ? a.diag_add + (a.diag_batched ? (long long)b0 * a.n : 0) : nullptr;
+  kp.sdiag = a.diag_batched ? a.n : 0;
+  kp.sigma_add = a.sigma_add ? a.sigma_add + (long long)b0 * a.n * a.n : nullptr;
+  kp.ssig = (long long)a.n * a.n;
+  kp.K = w.A; kp.n1 = a.n; kp.n2 = a.n; kp.d = a.d; kp.np1 = w.np; kp.np2 = w.np; kp.ldk = w.np;
+  kp.sK = (long long)w.np * w.np;
+  kp.symmetric = 1; kp.lower_only = 1; kp.clamp = a.clamp;
+  kernel_matrix_kernel<<<dim3(w.np / 64, w.np / 64, nb), 256, 0, st>>>(kp);
+  FFGP_CUDA(cudaGetLastError());
+  FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};
+  FFGP_CUDA(factor_rec(c, 0, w.np));
+  return 0;
+}
+
+// Gamma, rowsq, alpha for the chunk (alpha stays padded in the workspace)
+static int solve_rhs(const DenseArgs& a, const DenseWs& w, int b0, int nb, cudaStream_t st) {
+  const long long sM = (long long)w.np * w.np;
+  const double* y = a.y + (long long)b0 * a.n * a.D;
+  if (!w.gemm_rhs) {
+    const long long sG = (long long)w.np * a.D;
+    trmv_lower_kernel<8><<<dim3(w.np / 8, nb), 256, 0, st>>>(w.M, w.np, sM, y, a.n, a.D, (long long)a.n * a.D, w.Gm, sG,
+                                                             w.rowsq, w.np);
+    FFGP_CUDA(cudaGetLastError());
+    colsum_weighted_kernel<8><<<dim3(w.np / 32, nb), 256, 0, st>>>(w.M, w.np, sM, w.np, w.Gm, a.D, sG, a.D, w.alpha, a.D,
+                                                                   sG, w.np, 1, 0);
+    FFGP_CUDA(cudaGetLastError());
+  } else {
+    const long long sG = (long long)w.np * w.Dp;
+    dim3 blk(32, 8), grd((w.Dp + 31) / 32, (w.np + 7) / 8, nb);
+    pad_copy_kernel<<<grd, blk, 0, st>>>(y, a.n, a.D, a.D, (long long)a.n * a.D, w.Ypad, w.np, w.Dp, w.Dp, sG);
+    FFGP_CUDA(cudaGetLastError());
+    FFGP_CUDA(gemm(true, false, w.M, w.np, sM, w.Ypad, w.Dp, sG, w.Gm, w.Dp, sG, w.np, w.Dp, w.np, 1.0, 0.0, 0, K_LE_ROW,
+                   nb, st));
+    rowsq_kernel<<<dim3(w.np / 8, nb), 256, 0, st>>>(w.Gm, w.Dp, sG, w.Dp, w.rowsq, w.np);
+    FFGP_CUDA(cudaGetLastError());
+    FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.Gm, w.Dp, sG, w.alpha, w.Dp, sG, w.np, w.Dp, w.np, 1.0, 0.0, 0,
+                   K_GE_ROW, nb, st));
+  }
+  return 0;
+}
+
+static int copy_alpha_out(const DenseArgs& a, const DenseWs& w, int b0, int nb, double* out_alpha, cudaStream_t st) {
+  if (!out_alpha) return 0;
+  const int Dw = w.gemm_rhs ? w.Dp : a.D;
+  dim3 blk(32, 8), grd((a.D + 31) / 32, (a.n + 7) / 8, nb);
+  pad_copy_kernel<<<grd, blk, 0, st>>>(w.alpha, w.np, Dw, Dw, (long long)w.np * Dw,
+                                       out_alpha + (long long)b0 * a.n * a.D, a.n, a.D, a.D, (long long)a.n * a.D);
+  FFGP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ffgp
+
+using namespace ffgp;
+
+extern "C" {
+
+int ffgp_version(void) { return FFGP_VERSION; }
+const char* ffgp_last_error_string(void) { return g_err; }
+
+size_t ffgp_dense_workspace_bytes(int n, int d, int D, int ns, int batch) {
+  if (n <= 0 || D <= 0 || batch <= 0 || d < 0) return 0;
+  return layout_ws(n, d, D, ns, batch, nullptr).bytes;
+}
+
+int ffgp_kernel_matrix_f64(const double* x1, const double* x2, const double* inv_ls, const double* amp, int n1, int n2,
+                           int d, int batch, int params_batched, int clamp, double* K, void* stream) {
+  if (!x1 || !x2 || !inv_ls || !amp || !K) return fail(-1, "ffgp_kernel_matrix_f64: null pointer");
+  if (n1 <= 0 || n2 <= 0 || d <= 0 || batch <= 0) return fail(-2, "ffgp_kernel_matrix_f64: bad size");
+  cudaStream_t st = (cudaStream_t)stream;
+  KernelMatrixParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.x1 = x1; kp.x2 = x2; kp.sx1 = (long long)n1 * d; kp.sx2 = (long long)n2 * d;
+  kp.w = inv_ls; kp.sw = params_batched ? d : 0; kp.amp = amp; kp.samp = params_batched ? 1 : 0;
+  kp.K = K; kp.n1 = n1; kp.n2 = n2; kp.d = d;
+  kp.np1 = round_up(n1, 64); kp.np2 = round_up(n2, 64); kp.ldk = n2; kp.sK = (long long)n1 * n2;
+  kp.symmetric = 0; kp.lower_only = 0; kp.clamp = clamp; kp.bounded = 1;
+  kernel_matrix_kernel<<<dim3(kp.np2 / 64, kp.np1 / 64, batch), 256, 0, st>>>(kp);
+  FFGP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ffgp_dense_nll_f64(const double* x, const double* y, const double* inv_ls, const double* amp, const double* diag_add,
+                       const double* sigma_add, int n, int d, int D, int batch, int params_batched, int clamp,
+                       int want_grad, void* workspace, size_t workspace_bytes, double* out_nll, double* out_logdet,
+                       double* out_alpha, double* g_inv_ls, double* g_amp, double* g_diag, double* g_sigma, int* info,
+                       void* stream) {
+  if (!y || !workspace || !out_nll || !info) return fail(-1, "ffgp_dense_nll_f64: null pointer");
+  if (amp && (!x || !inv_ls)) return fail(-1, "ffgp_dense_nll_f64: kernel term needs x and inv_ls");
+  if (!amp && !sigma_add) return fail(-1, "ffgp_dense_nll_f64: neither a kernel nor a covariance was given");
+  if (n <= 0 || D <= 0 || batch <= 0 || d < 0) return fail(-2, "ffgp_dense_nll_f64: bad size");
+  if (amp && d > GRAD_DMAX && want_grad) return fail(-2, "ffgp_dense_nll_f64: d > 64 not supported with want_grad");
+  if (want_grad && amp && (!g_inv_ls || !g_amp)) return fail(-1, "ffgp_dense_nll_f64: gradient outputs missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  DenseWs w = layout_ws(n, d, D, 0, batch, (char*)workspace);
+  if (workspace_bytes < w.bytes) return fail(-3, "ffgp_dense_nll_f64: workspace too small");
+  FFGP_CUDA(ensure_attrs());
+  DenseArgs a{x, y, inv_ls, amp, diag_add, sigma_add, n, d, D, batch, params_batched, /*diag_batched=*/params_batched, clamp};
+  FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+  const long long sM = (long long)w.np * w.np;
+  for (int b0 = 0; b0 < batch; b0 += w.chunk) {
+    const int nb = std::min(w.chunk, batch - b0);
+    int rc;
+    if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
+    if ((rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
+    nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, D, out_nll + b0,
+                                          out_logdet ? out_logdet + b0 : nullptr);
+    FFGP_CUDA(cudaGetLastError());
+    if ((rc = copy_alpha_out(a, w, b0, nb, out_alpha, st)) != 0) return rc;
+    if (!want_grad) continue;
+    // S = M^T M (lower) into the dead A buffer
+    FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
+    int src_is_G = 0;
+    if (w.gemm_rhs) {   // G = 0.5 (D S - alpha alpha^T) through the GEMM epilogue
+      const long long sG = (long long)w.np * w.Dp;
+      FFGP_CUDA(gemm(true, true, w.alpha, w.Dp, sG, w.alpha, w.Dp, sG, w.A, w.np, sM, w.np, w.np, w.Dp, -0.5, 0.5 * D, 1,
+                     K_FULL, nb, st));
+      src_is_G = 1;
+    }
+    GradParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.src = w.A; gp.ld = w.np; gp.ssrc = sM;
+    gp.x = x ? x + (long long)b0 * n * d : nullptr; gp.n = n; gp.d = amp ? d : 0; gp.sx = (long long)n * d;
+    gp.w = inv_ls ? inv_ls + (params_batched ? (long long)b0 * d : 0) : nullptr; gp.sw = params_batched ? d : 0;
+    gp.amp = amp ? amp + (params_batched ? b0 : 0) : nullptr; gp.samp = params_batched ? 1 : 0;
+    gp.alpha = w.alpha; gp.D = D; gp.salpha = (long long)w.np * D;
+    gp.src_is_G = src_is_G;
+    gp.partial = w.partial; gp.npart = w.ngtile;
+    gp.g_diag = g_diag ? g_diag + (long long)b0 * n : nullptr; gp.sgd = n;
+    gp.G_out = g_sigma ? g_sigma + (long long)b0 * n * n : nullptr; gp.sGo = (long long)n * n;
+    gp.have_k = amp ? 1 : 0;
+    grad_contract_kernel<<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
+    FFGP_CUDA(cudaGetLastError());
+    if (amp) {
+      grad_finish_kernel<<<nb, 128, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,
+                                             g_inv_ls + (long long)b0 * d, g_amp + b0);
+      FFGP_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, const double* inv_ls, const double* amp,
+                           const double* diag_add, const double* sigma_add, const double* Ks, const double* Kss,
+                           const double* cov_offset, int n, int d, int D, int ns, int batch, int params_batched,
+                           int clamp, int full_cov, int reuse_factor, void* workspace, size_t workspace_bytes,
+                           double* out_mean, double* out_cov, int* info, void* stream) {
+  if (!y || !workspace || !out_mean || !info) return fail(-1, "ffgp_dense_predict_f64: null pointer");
+  if (amp && (!x || !xs || !inv_ls)) return fail(-1, "ffgp_dense_predict_f64: kernel term needs x, xs and inv_ls");
+  if (!amp && (!sigma_add || !Ks)) return fail(-1, "ffgp_dense_predict_f64: covariance mode needs sigma_add and Ks");
+  if (!amp && out_cov && !Kss) return fail(-1, "ffgp_dense_predict_f64: covariance mode needs Kss for out_cov");
+  if (!amp && out_cov && !full_cov) return fail(-2, "ffgp_dense_predict_f64: covariance mode returns the full covariance");
+  if (n <= 0 || D <= 0 || batch <= 0 || ns <= 0 || d < 0) return fail(-2, "ffgp_dense_predict_f64: bad size");
+  cudaStream_t st = (cudaStream_t)stream;
+  DenseWs w = layout_ws(n, d, D, ns, batch, (char*)workspace);
+  if (workspace_bytes < w.bytes) return fail(-3, "ffgp_dense_predict_f64: workspace too small");
+  if (reuse_factor && batch > w.chunk) return fail(-4, "ffgp_dense_predict_f64: reuse_factor needs batch <= one chunk");
+  FFGP_CUDA(ensure_attrs());
+  DenseArgs a{x, y, inv_ls, amp, diag_add, sigma_add, n, d, D, batch, params_batched, params_batched, clamp};
+  if (!reuse_factor) FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+  const long long sM = (long long)w.np * w.np, sKx = (long long)w.np * w.nsp, sKxx = (long long)w.nsp * w.nsp;
+  for (int b0 = 0; b0 < batch; b0 += w.chunk) {
+    const int nb = std::min(w.chunk, batch - b0);
+    int rc;
+    if (!reuse_factor) {
+      if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
+      if ((rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
+    }
+    // Kx = K(x, xs)  [np][nsp]   (or the caller's Ks, padded)
+    KernelMatrixParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.n1 = n; kp.n2 = ns; kp.d = d; kp.np1 = w.np; kp.np2 = w.nsp; kp.ldk = w.nsp; kp.sK = sKx; kp.K = w.Kx;
+    kp.clamp = clamp;
+    if (amp) {
+      kp.x1 = x + (long long)b0 * n * d; kp.sx1 = (long long)n * d;
+      kp.x2 = xs + (long long)b0 * ns * d; kp.sx2 = (long long)ns * d;
+      kp.w = inv_ls + (params_batched ? (long long)b0 * d : 0); kp.sw = params_batched ? d : 0;
+      kp.amp = amp + (params_batched ? b0 : 0); kp.samp = params_batched ? 1 : 0;
+    } else {
+      kp.sigma_add = Ks + (long long)b0 * n * ns; kp.ssig = (long long)n * ns;
+    }
+    kernel_matrix_kernel<<<dim3(w.nsp / 64, w.np / 64, nb), 256, 0, st>>>(kp);
+    FFGP_CUDA(cudaGetLastError());
+    // mean = Kx^T alpha
+    if (!w.gemm_rhs) {
+      colsum_weighted_kernel<8><<<dim3(w.nsp / 32, nb), 256, 0, st>>>(w.Kx, w.nsp, sKx, w.np, w.alpha, D,
+                                                                      (long long)w.np * D, D,
+                                                                      out_mean + (long long)b0 * ns * D, D,
+                                                                      (long long)ns * D, ns, 0, 0);
+      FFGP_CUDA(cudaGetLastError());
+    } else {
+      const long long sG = (long long)w.np * w.Dp, sMp = (long long)w.nsp * w.Dp;
+      FFGP_CUDA(gemm(false, false, w.Kx, w.nsp, sKx, w.alpha, w.Dp, sG, w.meanp, w.Dp, sMp, w.nsp, w.Dp, w.np, 1.0, 0.0, 0,
+                     K_FULL, nb, st));
+      dim3 blk(32, 8), grd((D + 31) / 32, (ns + 7) / 8, nb);
+      pad_copy_kernel<<<grd, blk, 0, st>>>(w.meanp, w.nsp, w.Dp, w.Dp, sMp, out_mean + (long long)b0 * ns * D, ns, D, D,
+                                           (long long)ns * D);
+      FFGP_CUDA(cudaGetLastError());
+    }
+    if (!out_cov) continue;
+    // V = M Kx
+    FFGP_CUDA(gemm(true, false, w.M, w.np, sM, w.Kx, w.nsp, sKx, w.V, w.nsp, sKx, w.np, w.nsp, w.np, 1.0, 0.0, 0, K_LE_ROW,
+                   nb, st));
+    if (full_cov) {
+      KernelMatrixParams kq;
+      memset(&kq, 0, sizeof(kq));
+      kq.n1 = ns; kq.n2 = ns; kq.d = d; kq.np1 = w.nsp; kq.np2 = w.nsp; kq.ldk = w.nsp; kq.sK = sKxx; kq.K = w.Kxx;
+      kq.clamp = clamp;
+      if (amp) {
+        kq.x1 = kq.x2 = xs + (long long)b0 * ns * d; kq.sx1 = kq.sx2 = (long long)ns * d;
+        kq.w = kp.w; kq.sw = kp.sw; kq.amp = kp.amp; kq.samp = kp.samp;
+      } else {
+        kq.sigma_add = Kss + (long long)b0 * ns * ns; kq.ssig = (long long)ns * ns;
+      }
+      kq.offset = cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr; kq.soff = params_batched ? 1 : 0;
+      kernel_matrix_kernel<<<dim3(w.nsp / 64, w.nsp / 64, nb), 256, 0, st>>>(kq);
+      FFGP_CUDA(cudaGetLastError());
+      // cov = Kxx - V^T V
+      FFGP_CUDA(gemm(false, false, w.V, w.nsp, sKx, w.V, w.nsp, sKx, w.Kxx, w.nsp, sKxx, w.nsp, w.nsp, w.np, -1.0, 1.0, 0,
+                     K_FULL, nb, st));
+      dim3 blk(32, 8), grd((ns + 31) / 32, (ns + 7) / 8, nb);
+      unpad_copy_kernel<<<grd, blk, 0, st>>>(w.Kxx, w.nsp, sKxx, out_cov + (long long)b0 * ns * ns, ns, ns,
+                                             (long long)ns * ns);
+      FFGP_CUDA(cudaGetLastError());
+    } else {
+      colsum_weighted_kernel<1><<<dim3(w.nsp / 32, nb), 256, 0, st>>>(w.V, w.nsp, sKx, w.np, nullptr, 0, 0, 1, w.colsq, 1,
+                                                                      w.nsp, w.nsp, 0, 1);
+      FFGP_CUDA(cudaGetLastError());
+      var_diag_kernel<<<dim3((ns + 127) / 128, nb), 128, 0, st>>>(w.colsq, amp + (params_batched ? b0 : 0),
+                                                                  params_batched ? 1 : 0,
+                                                                  cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr,
+                                                                  params_batched ? 1 : 0, out_cov + (long long)b0 * ns, ns);
+      FFGP_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+int ffgp_potrf_trtri_f64(const double* A, int n, int batch, void* workspace, size_t workspace_bytes, double* L,
+                         double* Linv, double* logdet, int* info, void* stream) {
+  if (!A || !workspace || !info) return fail(-1, "ffgp_potrf_trtri_f64: null pointer");
+  if (n <= 0 || batch <= 0) return fail(-2, "ffgp_potrf_trtri_f64: bad size");
+  cudaStream_t st = (cudaStream_t)stream;
+  DenseWs w = layout_ws(n, 0, 1, 0, batch, (char*)workspace);
+  if (workspace_bytes < w.bytes) return fail(-3, "ffgp_potrf_trtri_f64: workspace too small");
+  FFGP_CUDA(ensure_attrs());
+  DenseArgs a{nullptr, nullptr, nullptr, nullptr, nullptr, A, n, 0, 1, batch, 0, 0, 0};
+  FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+  for (int b0 = 0; b0 < batch; b0 += w.chunk) {
+    const int nb = std::min(w.chunk, batch - b0);
+    int rc;
+    if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
+    dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8, nb);
+    if (L) {
+      unpad_copy_kernel<<<grd, blk, 0, st>>>(w.L, w.np, (long long)w.np * w.np, L + (long long)b0 * n * n, n, n, (long long)n * n);
+      FFGP_CUDA(cudaGetLastError());
+    }
+    if (Linv) {
+      unpad_copy_kernel<<<grd, blk, 0, st>>>(w.M, w.np, (long long)w.np * w.np, Linv + (long long)b0 * n * n, n, n, (long long)n * n);
+      FFGP_CUDA(cudaGetLastError());
+    }
+    if (logdet) {
+      // rowsq is unused here: zero it so the reducer returns logdet only
+      FFGP_CUDA(cudaMemsetAsync(w.rowsq, 0, sizeof(double) * (size_t)nb * w.np, st));
+      nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, 1, nullptr, logdet + b0);
+      FFGP_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

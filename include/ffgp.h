@@ -1,0 +1,146 @@
+/* libffgp - B200 (sm_100a) Gaussian-process hot path behind FidelityFusion's operator API.
+ *
+ * C ABI (plain pointers and sizes, no torch types).  Every pointer is a DEVICE pointer unless
+ * marked host.  The caller owns every buffer, including the opaque workspace whose size is
+ * returned by the *_workspace_bytes queries; the library allocates nothing and keeps no pointer
+ * after a call returns.  All work is enqueued on `stream` (a cudaStream_t passed as void*) and
+ * there is no host synchronisation inside the library.  Matrices are row-major fp64.
+ *
+ * Return value: 0 = enqueued; <0 = bad argument / CUDA error (see ffgp_last_error_string()).
+ * Numerical failure (leading minor not positive definite) is reported LAPACK-style through the
+ * device array `info[batch]` (0 = ok, k>0 = minor k), which the host checks after the stream
+ * has drained - the Python layer turns it into torch.linalg.LinAlgError, which is what
+ * torch.linalg.cholesky raises in the reference.
+ *
+ * The reference has no FFI layer of its own (it is pure PyTorch); each entry point below
+ * replaces the chain of torch calls cited next to it.  Paths are relative to the reference
+ * root (IceLab-X/FidelityFusion).
+ */
+#ifndef FFGP_H
+#define FFGP_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFGP_VERSION 100
+
+int ffgp_version(void);
+const char* ffgp_last_error_string(void);  /* host string, thread-local */
+
+/* ---------------------------------------------------------------------------------------
+ * Stationary squared-exponential family, one parameterisation for the reference's three:
+ *   K[i][j] = amp * exp(-0.5 * sum_k ((x1[i][k] - x2[j][k]) * inv_ls[k])^2)
+ *   ARDKernel                 GaussianProcess/kernel.py:100-105   inv_ls = 1/(|p|+eps), amp = |s|, clamp=1 (cdist)
+ *   SquaredExponentialKernel  GaussianProcess/kernel.py:271-272   inv_ls = exp(-l),     amp = exp(s)^2
+ *   SE_kernel                 MFGP_ver2023May/kernel/SE_kernel.py:20-44  inv_ls = exp(-p) or 1/p, amp = exp(q) or q
+ * x1 [batch][n1][d], x2 [batch][n2][d], K [batch][n1][n2].  inv_ls [d] and amp [1] are shared by
+ * the batch when params_batched == 0, else [batch][d] / [batch].
+ * --------------------------------------------------------------------------------------- */
+int ffgp_kernel_matrix_f64(const double* x1, const double* x2, const double* inv_ls, const double* amp,
+                           int n1, int n2, int d, int batch, int params_batched, int clamp,
+                           double* K, void* stream);
+
+/* d(sum(gK o K))/d(inv_ls, amp) for the kernel above (autograd of a stand-alone kernel call).
+ * gK [batch][n1][n2]; g_inv_ls [batch][d]; g_amp [batch].  scratch: ffgp_kernel_matrix_bwd_scratch_bytes(). */
+size_t ffgp_kernel_matrix_bwd_scratch_bytes(int n1, int n2, int d, int batch);
+int ffgp_kernel_matrix_bwd_f64(const double* x1, const double* x2, const double* inv_ls, const double* amp,
+                               const double* gK, int n1, int n2, int d, int batch, int params_batched,
+                               double* g_inv_ls, double* g_amp, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense GP negative log marginal likelihood (+ analytic gradient), `batch` independent problems.
+ *   Sigma = K(x,x) + diag(diag_add) + sigma_add ;  L = chol(Sigma) ;  Gamma = L^-1 y
+ *   out_nll[b] = 0.5*||Gamma||_F^2 + D * sum_i log L_ii          (the 0.5*n*D*log(2*pi') constant is
+ *                                                                  added by the caller: the reference
+ *                                                                  uses 3.1415 or math.pi per path)
+ * Replaces: cigp.negative_log_likelihood  GaussianProcess/cigp_v10.py:50-69
+ *           CIGP.compute_loss             MFGP_ver2023May/base_gp/cigp.py:99-136
+ *           Gaussian_log_likelihood       GaussianProcess/gp_computation_pack.py:34-91 (amp == NULL: Sigma = sigma_add)
+ *           GP_basic.log_likelihood       GaussianProcess/gp_basic.py:94-153
+ *           and, with want_grad, their autograd backward (LinalgCholeskyExBackward0, TriangularSolveBackward0,
+ *           CdistBackward0 ...) through the closed form G = dNLL/dSigma = 0.5*(D*Sigma^-1 - alpha alpha^T).
+ * Inputs : x [batch][n][d]; y [batch][n][D]; inv_ls/amp as above (amp == NULL => no kernel term);
+ *          diag_add [n] or [batch][n] or NULL (noise + jitter + diag(y_var)); sigma_add [batch][n][n] or NULL.
+ * Outputs: out_nll [batch]; out_logdet [batch] or NULL (= 2 sum log L_ii);
+ *          out_alpha [batch][n][D] = Sigma^-1 y (= dNLL/dy ... with sign: dNLL/dy = alpha);
+ *          with want_grad: g_inv_ls [batch][d], g_amp [batch], g_diag [batch][n] (= G_ii),
+ *          g_sigma [batch][n][n] or NULL (full G, for callers that differentiate a given covariance).
+ *          info [batch] int.
+ * --------------------------------------------------------------------------------------- */
+size_t ffgp_dense_workspace_bytes(int n, int d, int D, int ns, int batch);
+
+int ffgp_dense_nll_f64(const double* x, const double* y, const double* inv_ls, const double* amp,
+                       const double* diag_add, const double* sigma_add,
+                       int n, int d, int D, int batch, int params_batched, int clamp, int want_grad,
+                       void* workspace, size_t workspace_bytes,
+                       double* out_nll, double* out_logdet, double* out_alpha,
+                       double* g_inv_ls, double* g_amp, double* g_diag, double* g_sigma,
+                       int* info, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Posterior mean / covariance at xs [batch][ns][d].
+ *   V = L^-1 K(x,xs);  mean = K(x,xs)^T Sigma^-1 y;  cov = K(xs,xs) - V^T V + cov_offset
+ * Replaces: cigp.forward            GaussianProcess/cigp_v10.py:24-48   (full_cov=1, cov_offset = e^-log_beta on EVERY entry)
+ *           CIGP.forward            MFGP_ver2023May/base_gp/cigp.py:61-97 (full_cov=0: diagonal + 1/beta)
+ *           conditional_Gaussian    GaussianProcess/gp_computation_pack.py:93-118 (amp == NULL: K_s, K_ss given)
+ *           GP_basic.forward        GaussianProcess/gp_basic.py:40-92
+ * reuse_factor != 0: the workspace still holds L^-1 and alpha of the same training problem from the
+ * previous ffgp_dense_nll_f64 / ffgp_dense_predict_f64 call (factor caching);
+ * batch must then fit in one workspace chunk.
+ * amp == NULL: Ks [batch][n][ns] and Kss [batch][ns][ns] (or NULL when only the mean is wanted) are given.
+ * out_mean [batch][ns][D]; out_cov [batch][ns][ns] (full_cov) or [batch][ns] (diagonal).
+ * --------------------------------------------------------------------------------------- */
+int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs,
+                           const double* inv_ls, const double* amp, const double* diag_add, const double* sigma_add,
+                           const double* Ks, const double* Kss, const double* cov_offset,
+                           int n, int d, int D, int ns, int batch, int params_batched, int clamp,
+                           int full_cov, int reuse_factor,
+                           void* workspace, size_t workspace_bytes,
+                           double* out_mean, double* out_cov, int* info, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Cholesky factor and triangular inverse of `batch` SPD matrices (row-major, lower).
+ * Replaces torch.linalg.cholesky + L.inverse() (cigp.py:129-131, gp_computation_pack.py:108-109).
+ * A [batch][n][n] (only the lower triangle is read); L, Linv [batch][n][n] (either may be NULL).
+ * --------------------------------------------------------------------------------------- */
+int ffgp_potrf_trtri_f64(const double* A, int n, int batch, void* workspace, size_t workspace_bytes,
+                         double* L, double* Linv, double* logdet, int* info, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * n-mode product (tensorly.tenalg.mode_dot; call sites hogp.py:132,181,183,187,217,236,
+ * multiscale_coupling/matrix.py:73,81, gp_computation_pack.py:157):
+ *   out[.., j, ..] = sum_i mat[j][i] * t[.., i, ..]  along `mode` of a contiguous tensor viewed as
+ *   [outer][I][inner];  mat is [J][I] (transpose_mat == 0) or [I][J] (transpose_mat != 0).
+ * --------------------------------------------------------------------------------------- */
+int ffgp_mode_dot_f64(const double* t, const double* mat, double* out,
+                      long long outer, int I, long long inner, int J, int transpose_mat, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Symmetric eigendecomposition of `batch` small matrices (cyclic Jacobi in shared memory),
+ * ascending eigenvalues like torch.linalg.eigh(K, UPLO='U') (hogp.py:18-22).  n <= 512.
+ * A [batch][n][n] is read from the UPPER triangle; w [batch][n]; V [batch][n][n] (columns = vectors).
+ * --------------------------------------------------------------------------------------- */
+size_t ffgp_syevj_workspace_bytes(int n, int batch);
+int ffgp_syevj_f64(const double* A, int n, int batch, double* w, double* V,
+                   void* workspace, size_t workspace_bytes, int* info, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Kronecker / Tucker GP (HOGP.compute_loss hogp.py:140-198, HOGP_simple.log_likelihood):
+ * given per-mode eigenpairs, in one pass over the data tensor:
+ *   A = kron(lambda_0..lambda_M) + noise_inv (+ y_var_scalar)   T1 = Y x_k U_k^T   (caller: mode products)
+ *   fused elementwise/reduction stage:  g_core = T1 / A ;  quad = sum T1^2 / A ;  logA = sum log A
+ * T1 [total]; lambdas are given as one concatenated array with `nmodes` sizes.
+ * out_core [total] (= T1 o A^-1), out_A [total] or NULL, out_sums[2] = {sum log A, sum T1^2/A}.
+ * --------------------------------------------------------------------------------------- */
+int ffgp_kron_core_f64(const double* T1, const double* lambdas, const int* sizes_host, int nmodes,
+                       const double* noise_inv, double add_scalar,
+                       double* out_core, double* out_A, double* out_sums, void* scratch, size_t scratch_bytes,
+                       void* stream);
+size_t ffgp_kron_core_scratch_bytes(long long total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFGP_H */
