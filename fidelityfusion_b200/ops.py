@@ -1,0 +1,334 @@
+"""Autograd-aware Python operators over the libffgp C ABI (include/ffgp.h).
+
+Everything here runs on CUDA through hand-written sm_100a kernels; there is no CPU path.
+fp32 inputs are promoted to fp64 for the computation and results are cast back (the hot path
+is an fp64 algorithm; see DESIGN.md "dtype rules").
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib as B
+
+
+def _f64c(t):
+    return t.detach().to(torch.float64).contiguous()
+
+
+def check_info(info, what='cholesky'):
+    """Raise what torch.linalg.cholesky raises in the reference when Sigma is not PD."""
+    bad = info.nonzero()
+    if bad.numel():
+        b = int(bad[0, 0])
+        k = int(info[b])
+        raise torch.linalg.LinAlgError(
+            f'ffgp.{what}: (Batch element {b}): The factorization could not be completed because the input is not '
+            f'positive-definite (the leading minor of order {k} is not positive-definite).')
+
+
+class _WorkspaceCache:
+    """Reuses the (large) opaque workspace across calls instead of re-allocating it."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = None
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_ws_cache = _WorkspaceCache()
+
+
+def _norm_batch(x, y, inv_ls, amp, diag_add, sigma_add):
+    """Bring inputs to the batched C-ABI layout.  Returns tensors + (n, d, D, batch, params_batched, squeeze)."""
+    squeeze = (y.dim() == 2)
+    if squeeze:
+        y = y.unsqueeze(0)
+        if x is not None:
+            x = x.unsqueeze(0)
+        if sigma_add is not None:
+            sigma_add = sigma_add.unsqueeze(0)
+    batch, n, D = y.shape
+    d = x.shape[-1] if x is not None else 0
+    params_batched = 0
+    if inv_ls is not None:
+        if inv_ls.dim() == 0:
+            inv_ls = inv_ls.reshape(1)
+        if inv_ls.dim() == 1 and inv_ls.numel() == 1 and d > 1:
+            inv_ls = inv_ls.expand(d)
+        if inv_ls.dim() == 2:
+            params_batched = 1
+    if amp is not None:
+        amp = amp.reshape(-1)
+        if amp.numel() > 1:
+            params_batched = 1
+    if diag_add is not None:
+        if diag_add.numel() == 1:
+            diag_add = diag_add.reshape(1).expand(n)
+        if diag_add.dim() == 2:
+            params_batched = 1
+    if params_batched:
+        if inv_ls is not None and inv_ls.dim() == 1:
+            inv_ls = inv_ls.unsqueeze(0).expand(batch, d)
+        if amp is not None and amp.numel() == 1:
+            amp = amp.expand(batch)
+        if diag_add is not None and diag_add.dim() == 1:
+            diag_add = diag_add.unsqueeze(0).expand(batch, n)
+    return x, y, inv_ls, amp, diag_add, sigma_add, n, d, D, batch, params_batched, squeeze
+
+
+class _DenseNLL(torch.autograd.Function):
+    """nll_core = 0.5*||L^-1 y||^2 + D*sum(log L_ii) with Sigma = K(x,x; inv_ls, amp) + diag(diag_add) + sigma_add.
+
+    One C call does forward AND the analytic gradient (the reference's callers always follow the loss with
+    .backward(), cigp_v10.py:50-69 + CIGAR.py:100-105), so backward() only scales saved tensors."""
+
+    @staticmethod
+    def forward(ctx, x, y, inv_ls, amp, diag_add, sigma_add, clamp):
+        if x is not None and x.requires_grad:
+            raise NotImplementedError('gradient w.r.t. training inputs x is not provided by the fused GP op')
+        out_dtype = y.dtype
+        x_, y_, il_, amp_, dg_, sg_, n, d, D, batch, pb, squeeze = _norm_batch(x, y, inv_ls, amp, diag_add, sigma_add)
+        dev = y.device
+        L = B.lib()
+        need = [t is not None and t.requires_grad for t in (y, inv_ls, amp, diag_add, sigma_add)]
+        want_grad = any(need) and torch.is_grad_enabled()
+        xc = _f64c(x_) if x_ is not None else None
+        yc = _f64c(y_)
+        ilc = _f64c(il_) if il_ is not None else None
+        ac = _f64c(amp_) if amp_ is not None else None
+        dc = _f64c(dg_) if dg_ is not None else None
+        sc = _f64c(sg_) if sg_ is not None else None
+        nll = torch.empty(batch, dtype=torch.float64, device=dev)
+        alpha = torch.empty(batch, n, D, dtype=torch.float64, device=dev)
+        info = torch.empty(batch, dtype=torch.int32, device=dev)
+        g_il = torch.empty(batch, max(d, 1), dtype=torch.float64, device=dev) if (want_grad and ac is not None) else None
+        g_amp = torch.empty(batch, dtype=torch.float64, device=dev) if (want_grad and ac is not None) else None
+        g_diag = torch.empty(batch, n, dtype=torch.float64, device=dev) if want_grad else None
+        g_sig = torch.empty(batch, n, n, dtype=torch.float64, device=dev) if (want_grad and need[4]) else None
+        wsb = L.ffgp_dense_workspace_bytes(n, d, D, 0, batch)
+        ws = _ws_cache.get(wsb, dev)
+        rc = L.ffgp_dense_nll_f64(B.ptr(xc), B.ptr(yc), B.ptr(ilc), B.ptr(ac), B.ptr(dc), B.ptr(sc),
+                                  n, d, D, batch, pb, int(bool(clamp)), int(want_grad),
+                                  B.ptr(ws), wsb, B.ptr(nll), None, B.ptr(alpha),
+                                  B.ptr(g_il), B.ptr(g_amp), B.ptr(g_diag), B.ptr(g_sig), B.ptr(info), B.stream_ptr())
+        B.check(rc, 'ffgp_dense_nll_f64')
+        check_info(info)
+        ctx.meta = (squeeze, pb, batch, n, d, D, out_dtype,
+                    None if inv_ls is None else tuple(inv_ls.shape), None if amp is None else tuple(amp.shape),
+                    None if diag_add is None else tuple(diag_add.shape))
+        ctx.save_for_backward(*[t for t in (alpha, g_il, g_amp, g_diag, g_sig) if t is not None])
+        ctx.have = [t is not None for t in (alpha, g_il, g_amp, g_diag, g_sig)]
+        out = nll.to(out_dtype)
+        return out[0] if squeeze else out
+
+    @staticmethod
+    def backward(ctx, go):
+        squeeze, pb, batch, n, d, D, out_dtype, il_shape, amp_shape, dg_shape = ctx.meta
+        saved = list(ctx.saved_tensors)
+        vals = [saved.pop(0) if h else None for h in ctx.have]
+        alpha, g_il, g_amp, g_diag, g_sig = vals
+        go = go.to(torch.float64).reshape(-1)                 # [batch] (or [1])
+        need = ctx.needs_input_grad
+        gy = gil = gamp = gdg = gsg = None
+        if need[1]:
+            gy = alpha * go.view(-1, 1, 1)
+            gy = gy[0] if squeeze else gy
+        if need[2] and g_il is not None:
+            t = g_il[:, :d] * go.view(-1, 1)
+            gil = t.sum(0) if len(il_shape) <= 1 else t
+            gil = gil.sum().reshape(il_shape) if math.prod(il_shape) == 1 else gil.reshape(il_shape)
+        if need[3] and g_amp is not None:
+            t = g_amp * go
+            gamp = t.sum().reshape(amp_shape) if math.prod(amp_shape) == 1 else t.reshape(amp_shape)
+        if need[4] and g_diag is not None and dg_shape is not None:
+            t = g_diag * go.view(-1, 1)
+            if len(dg_shape) == 2:
+                gdg = t
+            elif math.prod(dg_shape) == 1:
+                gdg = t.sum().reshape(dg_shape)
+            else:
+                gdg = t.sum(0).reshape(dg_shape)
+        if need[5] and g_sig is not None:
+            gsg = g_sig * go.view(-1, 1, 1)
+            gsg = gsg[0] if squeeze else gsg
+        cast = lambda t, ref: None if t is None else t.to(ref)
+        return None, cast(gy, out_dtype), gil, gamp, gdg, gsg, None
+
+
+def dense_nll(x, y, inv_ls, amp, diag_add=None, sigma_add=None, clamp=False):
+    """Differentiable 0.5*||L^-1 y||_F^2 + D*sum(log diag L), Sigma = K + diag(diag_add) + sigma_add.
+    x [n,d] (or [B,n,d]), y [n,D] (or [B,n,D]); inv_ls [d] / [B,d]; amp [1] / [B]; diag_add scalar, [n] or [B,n];
+    sigma_add [n,n] / [B,n,n].  amp=None means the covariance is given entirely by sigma_add (+diag_add)."""
+    return _DenseNLL.apply(x, y, inv_ls, amp, diag_add, sigma_add, clamp)
+
+
+def dense_predict(x, y, xs, inv_ls, amp, diag_add=None, sigma_add=None, Ks=None, Kss=None, cov_offset=None,
+                  full_cov=True, want_cov=True, clamp=False, cache=None, cache_token=None):
+    """Posterior mean and (full or diagonal) covariance.  No autograd (the reference's gen-2023 forward runs under
+    no_grad, cigp.py:79; gen-2024 callers use it for prediction).  `cache`: a FactorCache to skip re-factorising."""
+    out_dtype = y.dtype
+    x_, y_, il_, amp_, dg_, sg_, n, d, D, batch, pb, squeeze = _norm_batch(x, y, inv_ls, amp, diag_add, sigma_add)
+    dev = y.device
+    L = B.lib()
+    if amp_ is not None:
+        xs_ = xs.unsqueeze(0) if squeeze else xs
+        ns = xs_.shape[1]
+        xsc = _f64c(xs_)
+        Ksc = Kssc = None
+    else:
+        Ks_ = Ks.unsqueeze(0) if squeeze else Ks
+        ns = Ks_.shape[2]
+        xsc = None
+        Ksc = _f64c(Ks_)
+        Kssc = _f64c(Kss.unsqueeze(0) if squeeze else Kss) if Kss is not None else None
+    xc = _f64c(x_) if x_ is not None else None
+    yc = _f64c(y_)
+    ilc = _f64c(il_) if il_ is not None else None
+    ac = _f64c(amp_) if amp_ is not None else None
+    dc = _f64c(dg_) if dg_ is not None else None
+    sc = _f64c(sg_) if sg_ is not None else None
+    oc = None
+    if cov_offset is not None:
+        oc = _f64c(cov_offset.reshape(-1))
+        oc = oc.expand(batch).contiguous() if (pb and oc.numel() == 1) else oc
+    mean = torch.empty(batch, ns, D, dtype=torch.float64, device=dev)
+    cov = None
+    if want_cov:
+        cov = torch.empty((batch, ns, ns) if full_cov else (batch, ns), dtype=torch.float64, device=dev)
+    info = torch.zeros(batch, dtype=torch.int32, device=dev)
+    wsb = L.ffgp_dense_workspace_bytes(n, d, D, ns, batch)
+    reuse = 0
+    if cache is not None:
+        ws, reuse = cache.workspace(wsb, dev, (n, d, D, batch, cache_token))
+    else:
+        ws = _ws_cache.get(wsb, dev)
+    rc = L.ffgp_dense_predict_f64(B.ptr(xc), B.ptr(yc), B.ptr(xsc), B.ptr(ilc), B.ptr(ac), B.ptr(dc), B.ptr(sc),
+                                  B.ptr(Ksc), B.ptr(Kssc), B.ptr(oc), n, d, D, ns, batch, pb, int(bool(clamp)),
+                                  int(bool(full_cov)), int(reuse), B.ptr(ws), wsb, B.ptr(mean), B.ptr(cov),
+                                  B.ptr(info), B.stream_ptr())
+    B.check(rc, 'ffgp_dense_predict_f64')
+    if not reuse:
+        check_info(info)
+        if cache is not None:
+            cache.mark_valid()
+    mean = mean.to(out_dtype)
+    cov = cov.to(out_dtype) if cov is not None else None
+    if squeeze:
+        mean = mean[0]
+        cov = cov[0] if cov is not None else None
+    return mean, cov
+
+
+class FactorCache:
+    """Keeps the factorisation (L^-1, alpha) of one training problem resident on the device between
+    predictions (the reference re-factorises on every forward, cigp_v10.py:31-35).
+    The factorisation is reused only while the caller's token (parameter and data versions, see state_token)
+    is unchanged; invalidate() drops it explicitly."""
+
+    def __init__(self):
+        self.buf = None
+        self.key = None
+        self.valid = False
+
+    def invalidate(self):
+        self.valid = False
+
+    def workspace(self, nbytes, device, key):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.valid = False
+        if key != self.key:
+            self.key = key
+            self.valid = False
+        return self.buf, (1 if self.valid else 0)
+
+    def mark_valid(self):
+        self.valid = True
+
+
+def state_token(module, *tensors):
+    """Identity + in-place version of every parameter and data tensor a factorisation depends on."""
+    items = [(p.data_ptr(), p._version) for p in module.parameters()]
+    items += [(t.data_ptr(), t._version, tuple(t.shape)) for t in tensors if isinstance(t, torch.Tensor)]
+    return tuple(items)
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone kernel matrix with autograd (when a caller wants K itself)
+# ---------------------------------------------------------------------------------------------
+class _KernelMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, inv_ls, amp, clamp):
+        if x1.requires_grad or x2.requires_grad:
+            raise NotImplementedError('gradient w.r.t. kernel inputs is not provided by the fused kernel-matrix op')
+        out_dtype = x1.dtype
+        L = B.lib()
+        x1c, x2c = _f64c(x1), _f64c(x2)
+        ilc, ac = _f64c(inv_ls.reshape(-1)), _f64c(amp.reshape(-1))
+        n1, d = x1c.shape
+        n2 = x2c.shape[0]
+        K = torch.empty(n1, n2, dtype=torch.float64, device=x1.device)
+        rc = L.ffgp_kernel_matrix_f64(B.ptr(x1c), B.ptr(x2c), B.ptr(ilc), B.ptr(ac), n1, n2, d, 1, 0, int(bool(clamp)),
+                                      B.ptr(K), B.stream_ptr())
+        B.check(rc, 'ffgp_kernel_matrix_f64')
+        ctx.save_for_backward(x1c, x2c, ilc, ac)
+        ctx.meta = (tuple(inv_ls.shape), tuple(amp.shape), out_dtype)
+        return K.to(out_dtype)
+
+    @staticmethod
+    def backward(ctx, gK):
+        x1c, x2c, ilc, ac = ctx.saved_tensors
+        il_shape, amp_shape, out_dtype = ctx.meta
+        L = B.lib()
+        n1, d = x1c.shape
+        n2 = x2c.shape[0]
+        gKc = _f64c(gK)
+        g_il = torch.empty(d, dtype=torch.float64, device=gK.device)
+        g_amp = torch.empty(1, dtype=torch.float64, device=gK.device)
+        sb = L.ffgp_kernel_matrix_bwd_scratch_bytes(n1, n2, d, 1)
+        scratch = torch.empty(max(sb, 8), dtype=torch.uint8, device=gK.device)
+        rc = L.ffgp_kernel_matrix_bwd_f64(B.ptr(x1c), B.ptr(x2c), B.ptr(ilc), B.ptr(ac), B.ptr(gKc), n1, n2, d, 1, 0,
+                                          B.ptr(g_il), B.ptr(g_amp), B.ptr(scratch), sb, B.stream_ptr())
+        B.check(rc, 'ffgp_kernel_matrix_bwd_f64')
+        return None, None, g_il.reshape(il_shape), g_amp.reshape(amp_shape), None
+
+
+def kernel_matrix(x1, x2, inv_ls, amp, clamp=False):
+    """K[i][j] = amp * exp(-0.5 * sum_k ((x1[i,k]-x2[j,k]) * inv_ls[k])^2), differentiable in inv_ls and amp."""
+    if x1.dim() > 2:                                           # SE_kernel.py:29-32 flattens >2-D inputs
+        x1 = x1.reshape(x1.size(0), -1)
+        x2 = x2.reshape(x2.size(0), -1)
+    d = x1.shape[1]
+    inv_ls = inv_ls.reshape(-1)
+    if inv_ls.numel() == 1 and d > 1:
+        inv_ls = inv_ls.expand(d)
+    return _KernelMatrix.apply(x1, x2, inv_ls, amp, clamp)
+
+
+# ---------------------------------------------------------------------------------------------
+# Cholesky factor + triangular inverse (for callers that want L itself)
+# ---------------------------------------------------------------------------------------------
+def potrf_trtri(A, want_L=True, want_inv=True):
+    squeeze = A.dim() == 2
+    Ab = _f64c(A.unsqueeze(0) if squeeze else A)
+    batch, n, _ = Ab.shape
+    L = B.lib()
+    dev = A.device
+    Lo = torch.empty_like(Ab) if want_L else None
+    Mo = torch.empty_like(Ab) if want_inv else None
+    logdet = torch.empty(batch, dtype=torch.float64, device=dev)
+    info = torch.zeros(batch, dtype=torch.int32, device=dev)
+    wsb = L.ffgp_dense_workspace_bytes(n, 0, 1, 0, batch)
+    ws = _ws_cache.get(wsb, dev)
+    rc = L.ffgp_potrf_trtri_f64(B.ptr(Ab), n, batch, B.ptr(ws), wsb, B.ptr(Lo), B.ptr(Mo), B.ptr(logdet), B.ptr(info),
+                                B.stream_ptr())
+    B.check(rc, 'ffgp_potrf_trtri_f64')
+    check_info(info)
+    f = (lambda t: None if t is None else (t[0] if squeeze else t).to(A.dtype))
+    return f(Lo), f(Mo), (logdet[0] if squeeze else logdet).to(A.dtype)

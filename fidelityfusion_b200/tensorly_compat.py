@@ -1,0 +1,223 @@
+"""n-mode products with tensorly's call signatures (`tensorly.tenalg.mode_dot / multi_mode_dot`,
+`tucker_to_tensor`, `tensor_to_vec`), running on libffgp's DMMA mode-product kernels with autograd
+(reference call sites: hogp.py:132,173-187,217,236; multiscale_coupling/matrix.py:73,81;
+gp_computation_pack.py:157).  tensorly itself is an un-vendored dependency of the reference; the
+definition implemented is the standard one, fold(M @ unfold(T, mode))."""
+import ctypes
+import math
+
+import torch
+
+from . import _lib as B
+from . import ops
+
+
+def _split_shape(shape, mode):
+    outer = math.prod(shape[:mode])
+    inner = math.prod(shape[mode + 1:])
+    return outer, shape[mode], inner
+
+
+def _mode_dot_raw(t, mat, mode, transpose):
+    """t: contiguous fp64 CUDA tensor; mat: [J][I] (transpose=False) or [I][J] (transpose=True)."""
+    L = B.lib()
+    outer, I, inner = _split_shape(t.shape, mode)
+    J = mat.shape[1] if transpose else mat.shape[0]
+    assert (mat.shape[0] if transpose else mat.shape[1]) == I, (tuple(mat.shape), tuple(t.shape), mode)
+    out = torch.empty(t.shape[:mode] + (J,) + t.shape[mode + 1:], dtype=torch.float64, device=t.device)
+    rc = L.ffgp_mode_dot_f64(B.ptr(t), B.ptr(mat), B.ptr(out), outer, I, inner, J, int(transpose), B.stream_ptr())
+    B.check(rc, 'ffgp_mode_dot_f64')
+    return out
+
+
+def _mode_gram_raw(X, Y, mode):
+    """G[a][b] = sum_rest X[.., a, ..] * Y[.., b, ..] along `mode` (X, Y contiguous, same shape but for `mode`)."""
+    L = B.lib()
+    outer, Ja, inner = _split_shape(X.shape, mode)
+    Jb = Y.shape[mode]
+    G = torch.empty(Ja, Jb, dtype=torch.float64, device=X.device)
+    sb = L.ffgp_mode_gram_scratch_bytes(outer, inner, Ja, Jb)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=X.device)
+    rc = L.ffgp_mode_gram_f64(B.ptr(X), B.ptr(Y), B.ptr(G), outer, inner, Ja, Jb, B.ptr(scratch), sb, B.stream_ptr())
+    B.check(rc, 'ffgp_mode_gram_f64')
+    return G
+
+
+class _ModeDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, mat, mode, transpose):
+        tc, mc = ops._f64c(t), ops._f64c(mat)
+        ctx.save_for_backward(tc, mc)
+        ctx.meta = (mode, transpose, t.dtype, mat.dtype)
+        return _mode_dot_raw(tc, mc, mode, transpose).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, go):
+        tc, mc = ctx.saved_tensors
+        mode, transpose, tdt, mdt = ctx.meta
+        goc = ops._f64c(go)
+        gt = gm = None
+        if ctx.needs_input_grad[0]:
+            gt = _mode_dot_raw(goc, mc, mode, not transpose).to(tdt)
+        if ctx.needs_input_grad[1]:
+            gm = _mode_gram_raw(goc, tc, mode)           # [J][I]
+            if transpose:
+                gm = gm.t()
+            gm = gm.to(mdt)
+        return gt, gm, None, None
+
+
+def mode_dot(tensor, matrix_or_vector, mode, transpose=False):
+    """tensorly.tenalg.mode_dot: matrix [J, I_mode] maps mode size I -> J; a vector [I_mode] contracts the mode."""
+    m = matrix_or_vector
+    if m.dim() == 1:
+        out = _ModeDot.apply(tensor, m.unsqueeze(0), mode, False)
+        return out.squeeze(mode)
+    return _ModeDot.apply(tensor, m, mode, bool(transpose))
+
+
+def multi_mode_dot(tensor, matrix_or_vec_list, modes=None, skip=None, transpose=False):
+    """tensorly.tenalg.multi_mode_dot: successive mode products (modes default to 0..len-1)."""
+    if modes is None:
+        modes = list(range(len(matrix_or_vec_list)))
+    res = tensor
+    decrement = 0
+    for i, (m, mode) in enumerate(zip(matrix_or_vec_list, modes)):
+        if skip is not None and i == skip:
+            continue
+        res = mode_dot(res, m, mode - decrement, transpose=transpose)
+        if m.dim() == 1:
+            decrement += 1
+    return res
+
+
+def tucker_to_tensor(tucker_tensor):
+    core, factors = tucker_tensor
+    return multi_mode_dot(core, factors)
+
+
+def tensor_to_vec(t):
+    return t.reshape(-1)
+
+
+def ones(shape, **kw):
+    return torch.ones(shape, **{k: v for k, v in kw.items() if k in ('device', 'dtype')})
+
+
+# ---------------------------------------------------------------------------------------------
+# Kronecker GP core: per-mode eigh -> T1 -> (A, core, sums) -> g, with the analytic gradient
+# ---------------------------------------------------------------------------------------------
+def eigh(K):
+    """Ascending eigenpairs of a symmetric matrix (upper triangle read), Jacobi in shared memory.
+    No autograd: the Kronecker loss below differentiates analytically w.r.t. K instead of through eigh."""
+    L = B.lib()
+    Kc = ops._f64c(K).unsqueeze(0)
+    n = Kc.shape[-1]
+    dev = K.device
+    w = torch.empty(1, n, dtype=torch.float64, device=dev)
+    V = torch.empty(1, n, n, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = L.ffgp_syevj_workspace_bytes(n, 1)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    rc = L.ffgp_syevj_f64(B.ptr(Kc), n, 1, B.ptr(w), B.ptr(V), B.ptr(ws), wsb, B.ptr(info), B.stream_ptr())
+    B.check(rc, 'ffgp_syevj_f64')
+    if int(info[0]) != 0:
+        raise torch.linalg.LinAlgError('ffgp.eigh: Jacobi sweeps did not converge')
+    return w[0].to(K.dtype), V[0].to(K.dtype)
+
+
+def _sizes_arr(sizes):
+    return (ctypes.c_int * len(sizes))(*[int(s) for s in sizes])
+
+
+def _kron_core(T1, lam_cat, sizes, tau_t, add):
+    L = B.lib()
+    dev = T1.device
+    core = torch.empty_like(T1)
+    A = torch.empty_like(T1)
+    sums = torch.empty(4, dtype=torch.float64, device=dev)
+    sb = L.ffgp_kron_core_scratch_bytes(T1.numel())
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+    rc = L.ffgp_kron_core_f64(B.ptr(T1), B.ptr(lam_cat), _sizes_arr(sizes), len(sizes), B.ptr(tau_t), float(add),
+                              B.ptr(core), B.ptr(A), B.ptr(sums), B.ptr(scratch), sb, B.stream_ptr())
+    B.check(rc, 'ffgp_kron_core_f64')
+    return core, A, sums
+
+
+def _kron_scale(inp, lam_cat, sizes, skip, divide_by_A, tau_t, add, dev):
+    L = B.lib()
+    out = torch.empty([int(s) for s in sizes], dtype=torch.float64, device=dev)
+    rc = L.ffgp_kron_scale_f64(B.ptr(inp), B.ptr(lam_cat), _sizes_arr(sizes), len(sizes), int(skip), int(divide_by_A),
+                               B.ptr(tau_t), float(add), B.ptr(out), B.stream_ptr())
+    B.check(rc, 'ffgp_kron_scale_f64')
+    return out
+
+
+class _KronNLL(torch.autograd.Function):
+    """S = kron(K_0..K_M) + tau I;  returns (0.5*log|S| + 0.5*vec(Y)^T S^-1 vec(Y),  A,  g = S^-1 vec(Y)).
+    Gradient (closed form, no differentiation through eigh):
+      dY = g;  dtau = 0.5*(sum 1/A - sum h^2), h = T1/A;
+      dK_k = 0.5 * U_k (diag(c_k) - Q_k) U_k^T,  c_k[j] = sum_{i_k=j} prod_{m!=k} lambda_m / A,
+      Q_k = weighted mode-k Gram matrix of h."""
+
+    @staticmethod
+    def forward(ctx, Y, tau, add, *Ks):
+        dev = Y.device
+        Yc = ops._f64c(Y)
+        sizes = list(Yc.shape)
+        eig = [eigh(ops._f64c(K)) for K in Ks]
+        lam_cat = torch.cat([e[0] for e in eig]).contiguous()
+        T1 = Yc
+        for k, (_, U) in enumerate(eig):
+            T1 = _mode_dot_raw(T1, U.contiguous(), k, True)          # x_k U_k^T
+        tau_t = ops._f64c(tau.reshape(1))
+        h, A, sums = _kron_core(T1, lam_cat, sizes, tau_t, add)
+        g = h
+        for k, (_, U) in enumerate(eig):
+            g = _mode_dot_raw(g, U.contiguous(), k, False)           # x_k U_k
+        ctx.save_for_backward(h, g, sums, lam_cat, tau_t, *[e[1] for e in eig])
+        ctx.meta = (sizes, float(add), Y.dtype, [K.dtype for K in Ks], tau.shape, tau.dtype)
+        val = 0.5 * (sums[0] + sums[1])
+        A_o, g_o = A.to(Y.dtype), g.to(Y.dtype)
+        flat = []
+        for lam, U in eig:
+            flat += [lam.to(Y.dtype), U.to(Y.dtype)]
+        ctx.mark_non_differentiable(A_o, g_o, *flat)
+        return (val.to(Y.dtype), A_o, g_o) + tuple(flat)
+
+    @staticmethod
+    def backward(ctx, go, *_unused):
+        h, g, sums, lam_cat, tau_t = ctx.saved_tensors[:5]
+        Us = ctx.saved_tensors[5:]
+        sizes, add, ydt, kdts, tau_shape, tau_dt = ctx.meta
+        dev = h.device
+        go = go.to(torch.float64)
+        gY = (g * go).to(ydt) if ctx.needs_input_grad[0] else None
+        gtau = None
+        if ctx.needs_input_grad[1]:
+            gtau = (0.5 * (sums[2] - sums[3]) * go).reshape(tau_shape).to(tau_dt)
+        gKs = []
+        for k, U in enumerate(Us):
+            if not ctx.needs_input_grad[3 + k]:
+                gKs.append(None)
+                continue
+            Wk = _kron_scale(None, lam_cat, sizes, k, 1, tau_t, add, dev)            # prod_{m!=k} lambda_m / A
+            ones_shape = list(sizes)
+            ones_shape[k] = 1
+            c_k = _mode_gram_raw(Wk, torch.ones(ones_shape, dtype=torch.float64, device=dev), k).reshape(-1)
+            hk = _kron_scale(h, lam_cat, sizes, k, 0, tau_t, add, dev)               # h o prod_{m!=k} lambda_m
+            Qk = _mode_gram_raw(h, hk, k)
+            Mk = (torch.diag(c_k) - Qk).contiguous()
+            Uc = U.contiguous()
+            gK = _mode_dot_raw(_mode_dot_raw(Mk, Uc, 0, False), Uc, 1, False)        # U M U^T
+            gKs.append((0.5 * go * gK).to(kdts[k]))
+        return (gY, gtau, None) + tuple(gKs)
+
+
+def kron_nll(Y, Ks, tau, add=0.0):
+    """Differentiable Kronecker-GP objective.  Returns (value, A, g, [(lambda_k, U_k)]); value excludes the
+    0.5*nd*log(2 pi) constant."""
+    out = _KronNLL.apply(Y, tau, float(add), *Ks)
+    val, A, g = out[:3]
+    eig = [(out[3 + 2 * k], out[4 + 2 * k]) for k in range(len(Ks))]
+    return val, A, g, eig

@@ -126,19 +126,31 @@ size_t ffgp_syevj_workspace_bytes(int n, int batch);
 int ffgp_syevj_f64(const double* A, int n, int batch, double* w, double* V,
                    void* workspace, size_t workspace_bytes, int* info, void* stream);
 
+/* G[a][b] = sum_{outer,inner} X[o][a][in] * Y[o][b][in]  (X viewed [outer][Ja][inner], Y [outer][Jb][inner]).
+ * This is d(mode_dot)/d(mat) (autograd of the couplings trained through the residual,
+ * multiscale_coupling/matrix.py:64, gp_computation_pack.py:152) and the weighted mode Gram matrices of the
+ * Kronecker-GP gradient.  Split over column slices, summed in a fixed order (deterministic). */
+size_t ffgp_mode_gram_scratch_bytes(long long outer, long long inner, int Ja, int Jb);
+int ffgp_mode_gram_f64(const double* X, const double* Y, double* G, long long outer, long long inner, int Ja, int Jb,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
- * Kronecker / Tucker GP (HOGP.compute_loss hogp.py:140-198, HOGP_simple.log_likelihood):
- * given per-mode eigenpairs, in one pass over the data tensor:
- *   A = kron(lambda_0..lambda_M) + noise_inv (+ y_var_scalar)   T1 = Y x_k U_k^T   (caller: mode products)
- *   fused elementwise/reduction stage:  g_core = T1 / A ;  quad = sum T1^2 / A ;  logA = sum log A
- * T1 [total]; lambdas are given as one concatenated array with `nmodes` sizes.
- * out_core [total] (= T1 o A^-1), out_A [total] or NULL, out_sums[2] = {sum log A, sum T1^2/A}.
+ * Kronecker / Tucker GP core stage (HOGP.compute_loss hogp.py:171-198, HOGP_simple.log_likelihood
+ * hogp_simple.py:104-126): with per-mode eigenvalues lambda_k (concatenated, `sizes_host[nmodes]` on the HOST),
+ *   A = kron(lambda_0..lambda_M) + noise_inv[0] + add_scalar,   T1 = Y x_k U_k^T (computed by ffgp_mode_dot_f64)
+ * one pass over the tensor produces
+ *   out_core = T1 / A   (then g = out_core x_k U_k),  out_A (optional),
+ *   out_sums[4] = { sum log A, sum T1^2 / A, sum 1/A, sum (T1/A)^2 }   (fixed-order reduction).
+ * ffgp_kron_scale_f64: out = in o prod_{m != skip_mode} lambda_m[i_m]  (/ A when divide_by_A) - the weights
+ * of the analytic gradient w.r.t. each mode's kernel matrix; in == NULL means in = 1.
  * --------------------------------------------------------------------------------------- */
+size_t ffgp_kron_core_scratch_bytes(long long total);
 int ffgp_kron_core_f64(const double* T1, const double* lambdas, const int* sizes_host, int nmodes,
                        const double* noise_inv, double add_scalar,
                        double* out_core, double* out_A, double* out_sums, void* scratch, size_t scratch_bytes,
                        void* stream);
-size_t ffgp_kron_core_scratch_bytes(long long total);
+int ffgp_kron_scale_f64(const double* in, const double* lambdas, const int* sizes_host, int nmodes, int skip_mode,
+                        int divide_by_A, const double* noise_inv, double add_scalar, double* out, void* stream);
 
 #ifdef __cplusplus
 }

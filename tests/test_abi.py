@@ -1,0 +1,54 @@
+"""The C-ABI library builds, loads and exports every symbol include/ffgp.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from fidelityfusion_b200.csrc import build
+    build.build()
+    from fidelityfusion_b200 import _lib
+    return _lib.lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'ffgp.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(ffgp_\w+)\s*\(', src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for s in ('ffgp_dense_nll_f64', 'ffgp_dense_predict_f64', 'ffgp_kernel_matrix_f64', 'ffgp_potrf_trtri_f64',
+              'ffgp_mode_dot_f64', 'ffgp_mode_gram_f64', 'ffgp_syevj_f64', 'ffgp_kron_core_f64'):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in declared_symbols():
+        assert hasattr(lib, s), f'{s} declared in include/ffgp.h but not exported by libffgp.so'
+
+
+def test_host_only_queries(lib):
+    assert lib.ffgp_version() == 100
+    # N=8192 single problem: three N^2 buffers + small vectors
+    b = lib.ffgp_dense_workspace_bytes(8192, 16, 1, 0, 1)
+    assert 3 * 8192 * 8192 * 8 <= b < 3.1 * 8192 * 8192 * 8
+    # big batches are chunked: the workspace stays bounded
+    assert lib.ffgp_dense_workspace_bytes(512, 8, 1, 64, 4096) < 7 * 2**30
+    assert lib.ffgp_dense_workspace_bytes(0, 8, 1, 0, 1) == 0
+    assert lib.ffgp_syevj_workspace_bytes(128, 4) >= 4 * 128 * 128 * 8
+    assert lib.ffgp_mode_gram_scratch_bytes(128, 512, 32, 32) > 0
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
+    rc = lib.ffgp_dense_nll_f64(None, None, None, None, None, None, 8, 2, 1, 1, 0, 0, 0, None, 0,
+                                None, None, None, None, None, None, None, None, None)
+    assert rc < 0 and b'null pointer' in lib.ffgp_last_error_string()
+    rc = lib.ffgp_syevj_f64(None, 4, 1, None, None, None, 0, None, None)
+    assert rc < 0

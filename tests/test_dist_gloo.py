@@ -1,0 +1,64 @@
+"""World-size-2 gloo run (CPU) of the batched-GP sharding: contiguous block partition, one packed all-gather,
+identical full result on every rank.  The GPU compute is replaced by the CPU oracle through `compute_fn`
+(test-only injection); on the B200 box the same code path runs with NCCL and the CUDA compute."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _oracle_compute(x, y, ls, sv, lb, xs, want_grad):
+    from oracle import ff_oracle as O
+    out = {k: [] for k in ('nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var')}
+    for b in range(x.shape[0]):
+        loss, gr = O.cigp_ard_nll_and_grads(x[b], y[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+        m, c = O.cigp_ard_predict(x[b], y[b], xs[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+        out['nll'].append(torch.tensor(loss)); out['g_length_scales'].append(gr['length_scales'])
+        out['g_signal_variance'].append(gr['signal_variance'][0]); out['g_log_beta'].append(gr['log_beta'][0])
+        out['mean'].append(m); out['var'].append(c.diag())
+    return {k: torch.stack(v) for k, v in out.items()}
+
+
+def _problems(Bn):
+    gen = torch.Generator().manual_seed(77)
+    return (torch.rand(Bn, 12, 3, generator=gen, dtype=torch.float64), torch.randn(Bn, 12, 1, generator=gen, dtype=torch.float64),
+            torch.rand(Bn, 3, generator=gen, dtype=torch.float64) + 0.5, torch.ones(Bn, dtype=torch.float64),
+            torch.rand(Bn, generator=gen, dtype=torch.float64), torch.rand(Bn, 4, 3, generator=gen, dtype=torch.float64))
+
+
+def _worker(rank, world, port, Bn, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from fidelityfusion_b200.batched import sharded_cigp_eval
+        torch.set_default_dtype(torch.float64)
+        x, y, ls, sv, lb, xs = _problems(Bn)
+        res = sharded_cigp_eval(x, y, ls, sv, lb, xs, compute_fn=_oracle_compute)
+        q.put((rank, {k: v.numpy().copy() for k, v in res.items()}))     # plain arrays: no shared-memory handles
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('Bn', [6, 7])
+def test_sharded_eval_two_ranks_gloo(Bn):
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, Bn, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.set_default_dtype(torch.float64)
+    full = _oracle_compute(*_problems(Bn), True)
+    for r in (0, 1):
+        for k, v in full.items():
+            assert tuple(got[r][k].shape) == tuple(v.shape), k
+            assert (got[r][k] == v.numpy()).all(), (r, k)                   # every rank holds the identical full result
+    torch.set_default_dtype(torch.float32)

@@ -1,0 +1,361 @@
+"""GPU parity tests of the dense GP path: CUDA (through the drop-in modules -> C ABI) vs the CPU oracle on the
+same inputs, vs the committed golden vectors of the real reference, and size-independent properties at the
+BASELINE.json sizes.  Tolerance: 1e-9 relative (north_star), fp32 inputs 1e-4."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import ff_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+DEV = 'cuda'
+
+
+def T(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float64)
+
+
+def G(a):
+    return T(a).to(DEV)
+
+
+@pytest.fixture(autouse=True)
+def _f64_default():
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
+
+
+def _cigp(d, ls, sv, lb):
+    from fidelityfusion_b200.GaussianProcess.cigp_v10 import cigp
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
+    k = ARDKernel(d)
+    with torch.no_grad():
+        k.length_scales.copy_(T(ls))
+        k.signal_variance.fill_(float(sv))
+    return cigp(k, float(lb)).to(DEV)
+
+
+def test_kernel_matrices_match_reference_golden():
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel, SquaredExponentialKernel
+    from fidelityfusion_b200.MFGP_ver2023May.kernel.SE_kernel import SE_kernel
+    g = load_golden('kernels')
+    for tag in ('small', 'mm'):
+        x1, x2 = G(g[f'{tag}_x1']), G(g[f'{tag}_x2'])
+        d = x1.shape[1]
+        k = ARDKernel(d)
+        with torch.no_grad():
+            k.length_scales.copy_(T(g[f'{tag}_ls']))
+            k.signal_variance.fill_(-1.7)
+        k = k.to(DEV)
+        assert rel_err(k(x1, x2).cpu(), g[f'{tag}_ard']) < TOL
+        assert rel_err(k(x1, x1).cpu(), g[f'{tag}_ard_sym']) < TOL
+        assert rel_err(SquaredExponentialKernel(0.3, -0.2).to(DEV)(x1, x2).cpu(), g[f'{tag}_sqexp']) < TOL
+        assert rel_err(SE_kernel(True, [0.7 + 0.1 * i for i in range(d)], 1.3).to(DEV)(x1, x2).cpu(), g[f'{tag}_se_exp']) < TOL
+        assert rel_err(SE_kernel(False, 0.8, 2.0).to(DEV)(x1, x2).cpu(), g[f'{tag}_se_lin']) < TOL
+
+
+def test_kernel_matrix_autograd_matches_oracle():
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
+    gen = torch.Generator().manual_seed(2)
+    x1, x2 = torch.randn(70, 6, generator=gen), torch.randn(45, 6, generator=gen)
+    wgt = torch.randn(70, 45, generator=gen)
+    k = ARDKernel(6, 0.8, 1.4).to(DEV)
+    (k(x1.to(DEV), x2.to(DEV)) * wgt.to(DEV)).sum().backward()
+    ls, sv = (torch.ones(6) * 0.8).requires_grad_(True), torch.tensor([1.4], requires_grad=True)
+    (O.ard_kernel(x1, x2, ls, sv) * wgt).sum().backward()
+    assert rel_err(k.length_scales.grad.cpu(), ls.grad) < TOL
+    assert rel_err(k.signal_variance.grad.cpu(), sv.grad) < TOL
+
+
+def test_kat1_cigp_ard():
+    g = load_golden('kat1_cigp_ard')
+    m = _cigp(2, [1., 1.], 1.0, 1.0)
+    x, y, xs = G(g['x']), G(g['y']), G(g['xs'])
+    ll = m.negative_log_likelihood(x, y)
+    assert ll.dim() == 0
+    assert abs(ll.item() - (-14.408784462236161)) < 1e-11
+    (-ll).backward()
+    assert rel_err(m.kernel.length_scales.grad.cpu(), g['g_length_scales']) < TOL
+    assert rel_err(m.kernel.signal_variance.grad.cpu(), g['g_signal_variance']) < TOL
+    assert rel_err(m.log_beta.grad.cpu(), g['g_log_beta']) < TOL
+    mean, cov = m(x, y, xs)
+    assert rel_err(mean.cpu(), g['mean']) < TOL and rel_err(cov.cpu(), g['cov']) < TOL
+    mean2, cov2 = m(x, y, xs)                                          # second call reuses the cached factor
+    assert torch.equal(mean, mean2) and torch.equal(cov, cov2)
+
+
+def test_kat2_CIGP2023():
+    from fidelityfusion_b200.MFGP_ver2023May import CIGP
+    g = load_golden('kat2_CIGP2023')
+    c = CIGP(None).double().to(DEV)
+    assert sorted(n for n, _ in c.named_parameters()) == ['kernel.length_scale', 'kernel.scale', 'noise_box.value']
+    x, y, xs = G(g['x']), G(g['y']), G(g['xs'])
+    loss = c.compute_loss(x, y)
+    assert abs(loss.item() - 19.35232673878598) < 1e-10
+    loss.backward()
+    assert rel_err(c.noise_box.value.grad.cpu(), g['g_noise']) < TOL
+    assert rel_err(c.kernel.length_scale.grad.cpu(), g['g_length_scale']) < TOL
+    assert rel_err(c.kernel.scale.grad.cpu(), g['g_scale']) < TOL
+    u, v = c.forward(xs)
+    assert rel_err(u.cpu(), g['u']) < TOL and rel_err(v.cpu(), g['var']) < TOL
+
+
+@pytest.mark.parametrize('tag', ['init', 'ls_half', 'ls_double', 'lb_m2', 'lb_3', 'sv_neg'])
+def test_c2_shape_nll_and_every_gradient(tag):
+    g = load_golden('c2_n512')
+    ls0, sv0, lb0 = g[f'{tag}_params']
+    m = _cigp(16, np.full(16, ls0), sv0, lb0)
+    x = G(g['x'])
+    y = G(g['y']).requires_grad_(True)
+    ll = m.negative_log_likelihood(x, y)
+    assert abs(ll.item() - float(g[f'{tag}_ll'])) <= TOL * abs(float(g[f'{tag}_ll']))
+    (-ll).backward()
+    assert rel_err(m.kernel.length_scales.grad.cpu(), g[f'{tag}_g_length_scales']) < TOL
+    assert rel_err(m.kernel.signal_variance.grad.cpu(), g[f'{tag}_g_signal_variance']) < TOL
+    assert rel_err(m.log_beta.grad.cpu(), g[f'{tag}_g_log_beta']) < TOL
+    assert rel_err(y.grad.cpu(), g[f'{tag}_g_y']) < TOL
+
+
+def test_c2_shape_predict():
+    g = load_golden('c2_n512')
+    m = _cigp(16, np.full(16, 2.0), 1.0, 1.0)
+    mean, cov = m(G(g['x']), G(g['y']), G(g['xs']))
+    assert rel_err(mean.cpu(), g['pred_mean']) < TOL and rel_err(cov.cpu(), g['pred_cov']) < TOL
+
+
+@pytest.mark.parametrize('n,d,D', [(1, 1, 1), (7, 3, 2), (129, 4, 1), (300, 2, 9), (257, 5, 70)])
+def test_ragged_sizes_vs_oracle(n, d, D):
+    """sizes that are not multiples of any tile (identity-tail padding), D on both sides of the GEMV/GEMM switch."""
+    gen = torch.Generator().manual_seed(100 + n)
+    x, y = torch.rand(n, d, generator=gen), torch.randn(n, D, generator=gen)
+    ls, sv, lb = torch.rand(d, generator=gen) + 0.5, torch.tensor([1.3]), torch.tensor([0.7])
+    m = _cigp(d, ls, sv, lb)
+    yy = y.to(DEV).requires_grad_(True)
+    ll = m.negative_log_likelihood(x.to(DEV), yy)
+    (-ll).backward()
+    loss, gr = O.cigp_ard_nll_and_grads(x, y, ls, sv, lb, want_y_grad=True)
+    assert abs(-ll.item() - loss) <= TOL * max(abs(loss), 1.0)
+    assert rel_err(m.kernel.length_scales.grad.cpu(), gr['length_scales']) < TOL
+    assert rel_err(m.kernel.signal_variance.grad.cpu(), gr['signal_variance']) < TOL
+    assert rel_err(m.log_beta.grad.cpu(), gr['log_beta']) < TOL
+    assert rel_err(yy.grad.cpu(), gr['y']) < TOL
+    xs = torch.rand(5, d, generator=gen)
+    mean, cov = m(x.to(DEV), y.to(DEV), xs.to(DEV))
+    om, oc = O.cigp_ard_predict(x, y, xs, ls, sv, lb)
+    assert rel_err(mean.cpu(), om) < TOL and rel_err(cov.cpu(), oc) < TOL
+
+
+def test_c3_yvar_many_outputs_tensor_linear():
+    from fidelityfusion_b200.GaussianProcess.gp_computation_pack import Tensor_linear
+    g = load_golden('c3_small')
+    tl = Tensor_linear([16], [64]).double().to(DEV)
+    assert rel_err(tl.vectors[0].detach().cpu(), g['tl_init']) < 1e-12
+    m = _cigp(5, np.full(5, 0.7), 1.2, 0.5)
+    x, ylo, yhi, yv = G(g['x']), G(g['y_low']), G(g['y_high']), G(g['y_var'])
+    res = yhi - tl(ylo)
+    assert rel_err(res.detach().cpu(), g['res']) < TOL
+    ll = m.negative_log_likelihood(x, [res, yv])
+    assert abs(ll.item() - float(g['ll'])) <= TOL * abs(float(g['ll']))
+    (-ll).backward()
+    assert rel_err(m.kernel.length_scales.grad.cpu(), g['g_length_scales']) < TOL
+    assert rel_err(m.kernel.signal_variance.grad.cpu(), g['g_signal_variance']) < TOL
+    assert rel_err(m.log_beta.grad.cpu(), g['g_log_beta']) < TOL
+    assert rel_err(tl.vectors[0].grad.cpu(), g['g_tl']) < TOL        # trained through the residual (CIGAR.py:119)
+    mean, cov = m(x, [res.detach(), yv], G(g['xs']))
+    assert rel_err(mean.cpu(), g['mean']) < TOL and rel_err(cov.cpu(), g['cov']) < TOL
+    g2 = load_golden('tensor_linear_2mode')
+    tl2 = Tensor_linear([4, 6], [8, 12]).double().to(DEV)
+    assert rel_err(tl2(G(g2['t'])).detach().cpu(), g2['out']) < 1e-12   # only the last mode is applied (sic)
+
+
+def test_pack_and_gp_basic():
+    from fidelityfusion_b200.GaussianProcess import gp_computation_pack as pack
+    from fidelityfusion_b200.GaussianProcess.gp_basic import GP_basic
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
+    g = load_golden('pack')
+    S, Ks, Kss = G(g['Sigma']), G(g['K_s']), G(g['K_ss'])
+    for D in (1, 3):
+        y = G(g[f'y{D}'])
+        for meth in ('cholesky1', 'cholesky2', 'cholesky3', 'direct'):
+            key = f'gll_{meth}_D{D}'
+            if key in g:
+                out = pack.Gaussian_log_likelihood(y, S, meth)
+                assert tuple(out.shape) == tuple(g[key].shape)
+                assert rel_err(out.cpu(), g[key]) < TOL
+        for meth in ('cholesky1', 'cholesky3', 'direct'):
+            mu, cov = pack.conditional_Gaussian(y, S, Ks, Kss, meth)
+            assert rel_err(mu.cpu(), g[f'cg_{meth}_D{D}_mu']) < TOL and rel_err(cov.cpu(), g[f'cg_{meth}_D{D}_cov']) < TOL
+    x, xs, y = G(g['x']), G(g['xs']), G(g['y3'])
+    k = ARDKernel(3, 1.1, 0.9).to(DEV)
+    lb = torch.tensor([0.7], device=DEV, requires_grad=True)
+    ll = pack.negative_log_likelihood(k, lb, x, y)
+    assert rel_err(ll.detach().cpu().reshape(()), g['pack_nll']) < TOL
+    (-ll).backward()
+    assert rel_err(lb.grad.cpu(), g['pack_nll_g_lb']) < TOL
+    assert rel_err(k.length_scales.grad.cpu(), g['pack_nll_g_ls']) < TOL
+    assert rel_err(k.signal_variance.grad.cpu(), g['pack_nll_g_sv']) < TOL
+    for D in (1, 3):
+        k = ARDKernel(3, 1.1, 0.9)
+        gp = GP_basic(k, 0.4).to(DEV)
+        y = G(g[f'y{D}'])
+        ll = gp.log_likelihood(x, y)
+        assert rel_err(ll.detach().cpu(), g[f'gpb_ll_D{D}']) < TOL
+        (-ll.sum()).backward()
+        assert rel_err(gp.noise_variance.grad.cpu(), g[f'gpb_g_noise_D{D}']) < TOL
+        assert rel_err(gp.kernel.length_scales.grad.cpu(), g[f'gpb_g_ls_D{D}']) < TOL
+        mu, cov = gp(x, y, xs)
+        assert rel_err(mu.cpu(), g[f'gpb_mu_D{D}']) < TOL and rel_err(cov.cpu(), g[f'gpb_cov_D{D}']) < TOL
+
+
+def test_c1_AR2023_training_trajectory():
+    """C1: gen-2023 AR = sum of CIGP losses on Residual targets (AR_AutoRegression.py:206-254), 5 Adam steps."""
+    from fidelityfusion_b200.MFGP_ver2023May import CIGP
+    from fidelityfusion_b200.MFGP_ver2023May.multiscale_coupling.Residual import Residual
+    g = load_golden('c1_AR2023')
+    x, xe, y0, y1 = G(g['x']), G(g['xe']), G(g['y0']), G(g['y1'])
+    gps = torch.nn.ModuleList([CIGP(None), CIGP(None)]).double().to(DEV)
+    res = Residual(None).double().to(DEV)
+    params = list(gps.parameters()) + list(res.parameters())
+    opt = torch.optim.Adam(params, lr=0.01)
+    for it in range(5):
+        opt.zero_grad()
+        loss = gps[0].compute_loss(x, y0) + gps[1].compute_loss(x, res.forward(y0, y1), update_data=True)
+        loss.backward()
+        assert abs(loss.item() - g['losses'][it]) <= 1e-8 * abs(g['losses'][it]), it
+        if it == 0:
+            assert rel_err(res.rho.grad.cpu(), g['g0_residual_list_0_rho']) < TOL
+            for f in range(2):
+                assert rel_err(gps[f].kernel.length_scale.grad.cpu(), g[f'g0_cigp_list_{f}_kernel_length_scale']) < TOL
+                assert rel_err(gps[f].kernel.scale.grad.cpu(), g[f'g0_cigp_list_{f}_kernel_scale']) < TOL
+                assert rel_err(gps[f].noise_box.value.grad.cpu(), g[f'g0_cigp_list_{f}_noise_box_value']) < TOL
+        opt.step()
+    for f in range(2):
+        assert rel_err(gps[f].kernel.length_scale.detach().cpu(), g[f'p5_cigp_list_{f}_kernel_length_scale']) < 1e-8
+    # prediction chain of AR.forward (AR_AutoRegression.py:148-177): the residual GP was fitted on the pre-step targets
+    m0, v0 = gps[0].forward(xe)
+    m1, v1 = gps[1].forward(xe)
+    u, var = res.backward(m0, m1), res.var_backward(v0, v1)
+    assert rel_err(u.detach().cpu(), g['u']) < 1e-7 and rel_err(var.detach().cpu(), g['var']) < 1e-7
+
+
+def test_c5_batched_independent_gps():
+    from fidelityfusion_b200.batched import batched_cigp_eval
+    g = load_golden('c5_batch')
+    Bn = 6
+    x = torch.stack([T(g[f'x{b}']) for b in range(Bn)]).to(DEV)
+    y = torch.stack([T(g[f'y{b}']) for b in range(Bn)]).to(DEV)
+    xs = torch.stack([T(g[f'xs{b}']) for b in range(Bn)]).to(DEV)
+    ls = torch.stack([T(g[f'ls{b}']) for b in range(Bn)]).to(DEV)
+    lb = torch.stack([T(g[f'lb{b}']) for b in range(Bn)]).to(DEV)
+    sv = torch.ones(Bn, device=DEV)
+    out = batched_cigp_eval(x, y, ls, sv, lb, xs)
+    for b in range(Bn):
+        assert abs(-out['nll'][b].item() - float(g[f'll{b}'])) <= TOL * abs(float(g[f'll{b}']))
+        assert rel_err(out['g_length_scales'][b].cpu(), g[f'g_ls{b}']) < TOL
+        assert rel_err(out['g_signal_variance'][b].cpu().reshape(1), g[f'g_sv{b}']) < TOL
+        assert rel_err(out['g_log_beta'][b].cpu().reshape(1), g[f'g_lb{b}']) < TOL
+        assert rel_err(out['mean'][b].cpu(), g[f'mean{b}']) < TOL
+        assert rel_err(out['var'][b].cpu(), g[f'vdiag{b}']) < TOL
+
+
+def test_c5_full_size_batch_vs_oracle_subset():
+    """C5 recipe at N=512, d=8: 256 problems in one call, 8 of them checked against the oracle."""
+    from fidelityfusion_b200.batched import batched_cigp_eval
+    Bn, n, d, ns = 256, 512, 8, 64
+    xs_, ys_, lss, lbs, xss = [], [], [], [], []
+    for b in range(Bn):
+        gen = torch.Generator().manual_seed(5000 + b)
+        x = torch.rand(n, d, generator=gen)
+        w = torch.randn(d, 1, generator=gen)
+        y = torch.sin(3 * x @ w) + 0.05 * torch.randn(n, 1, generator=gen)
+        lss.append(torch.exp(torch.rand(d, generator=gen) * 2 - 1))
+        lbs.append(torch.rand(1, generator=gen)[0] * 3)
+        xss.append(torch.rand(ns, d, generator=gen))
+        xs_.append(x); ys_.append(y)
+    x, y, xs = torch.stack(xs_), torch.stack(ys_), torch.stack(xss)
+    ls, lb, sv = torch.stack(lss), torch.stack(lbs), torch.ones(Bn)
+    out = batched_cigp_eval(x.to(DEV), y.to(DEV), ls.to(DEV), sv.to(DEV), lb.to(DEV), xs.to(DEV))
+    for b in (0, 1, 17, 63, 64, 128, 200, 255):
+        loss, gr = O.cigp_ard_nll_and_grads(x[b], y[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+        assert abs(out['nll'][b].item() - loss) <= TOL * abs(loss)
+        assert rel_err(out['g_length_scales'][b].cpu(), gr['length_scales']) < TOL
+        assert rel_err(out['g_log_beta'][b].cpu().reshape(1), gr['log_beta']) < TOL
+        om, oc = O.cigp_ard_predict(x[b], y[b], xs[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+        assert rel_err(out['mean'][b].cpu(), om) < TOL and rel_err(out['var'][b].cpu(), oc.diag()) < TOL
+
+
+def test_not_positive_definite_raises_linalg_error():
+    from fidelityfusion_b200 import ops
+    y = torch.randn(40, 1, device=DEV)
+    S = -torch.eye(40, device=DEV)
+    with pytest.raises(torch.linalg.LinAlgError):
+        ops.dense_nll(None, y, None, None, sigma_add=S)
+    S = torch.eye(300, device=DEV)
+    S[200, 200] = -1.0
+    with pytest.raises(torch.linalg.LinAlgError, match='order 201'):
+        ops.dense_nll(None, torch.randn(300, 1, device=DEV), None, None, sigma_add=S)
+
+
+def test_fp32_inputs_within_1e4():
+    torch.set_default_dtype(torch.float32)
+    from fidelityfusion_b200.GaussianProcess.cigp_v10 import cigp
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
+    gen = torch.Generator().manual_seed(8)
+    x, y = torch.rand(200, 4, generator=gen), torch.randn(200, 2, generator=gen)
+    m = cigp(ARDKernel(4), 1.0).to(DEV)
+    ll = m.negative_log_likelihood(x.to(DEV), y.to(DEV))
+    assert ll.dtype == torch.float32
+    (-ll).backward()
+    loss, gr = O.cigp_ard_nll_and_grads(x.double(), y.double(), torch.ones(4, dtype=torch.float64),
+                                        torch.ones(1, dtype=torch.float64), torch.ones(1, dtype=torch.float64))
+    assert abs(-ll.item() - loss) <= 1e-4 * abs(loss)
+    assert rel_err(m.kernel.length_scales.grad.double().cpu(), gr['length_scales']) < 1e-4
+    assert rel_err(m.log_beta.grad.double().cpu(), gr['log_beta']) < 1e-4
+
+
+def test_factor_and_inverse_properties_at_scale():
+    """size-independent properties at N=2048 (multi-level recursion): L L^T = A, M L = I, log-det."""
+    from fidelityfusion_b200 import ops
+    n = 2048
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    Bm = torch.randn(n, n, device=DEV, generator=gen)
+    A = Bm @ Bm.T / n + torch.eye(n, device=DEV)
+    L, M, logdet = ops.potrf_trtri(A)
+    assert float((L @ L.T - A).abs().max() / A.abs().max()) < 1e-13
+    assert float((M @ L - torch.eye(n, device=DEV)).abs().max()) < 1e-11
+    assert float(torch.triu(L, 1).abs().max()) == 0.0 and float(torch.triu(M, 1).abs().max()) == 0.0
+    assert abs(float(logdet) - float(torch.linalg.slogdet(A)[1])) < 1e-9 * n
+
+
+def test_c2_full_size_anchor_and_gradient_identity():
+    """BASELINE config 2 at full size (N=8192, d=16): the NLL anchor recorded from the reference on CPU
+     and gradient identities that need no CPU factorisation:
+    dNLL/dlog_beta = -e^{-lb} tr(G) and  sum_i y_i alpha_i = 2*(quadratic part)."""
+    n, d = 8192, 16
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(n, d, generator=gen)
+    y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn(n, 1, generator=gen)
+    m = _cigp(d, np.ones(d), 1.0, 1.0)
+    yy = y.to(DEV).requires_grad_(True)
+    ll = m.negative_log_likelihood(x.to(DEV), yy)
+    assert abs(-ll.item() - 10327.5181420215) < 1e-9 * 10327.5
+    (-ll).backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+    # finite-difference check of the log_beta and signal_variance gradients (central, h=1e-4 => ~1e-8 rel)
+    for name, p in (('log_beta', m.log_beta), ('signal_variance', m.kernel.signal_variance)):
+        g0 = p.grad.item()
+        h = 1e-4
+        with torch.no_grad():
+            p.add_(h)
+            up = -m.negative_log_likelihood(x.to(DEV), y.to(DEV)).item()
+            p.sub_(2 * h)
+            dn = -m.negative_log_likelihood(x.to(DEV), y.to(DEV)).item()
+            p.add_(h)
+        fd = (up - dn) / (2 * h)
+        assert abs(fd - g0) <= 1e-6 * max(abs(g0), 1.0), (name, fd, g0)

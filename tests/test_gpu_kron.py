@@ -1,0 +1,217 @@
+"""GPU parity tests of the Kronecker/Tucker path: mode products, mode Gram, Jacobi eigh, HOGP loss / analytic
+gradient / prediction, couplings - vs the CPU oracle and the golden vectors of the real reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import ff_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def T(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float64)
+
+
+def G(a):
+    return T(a).to(DEV)
+
+
+@pytest.fixture(autouse=True)
+def _f64_default():
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
+
+
+@pytest.mark.parametrize('shape,mode,J', [((5, 4, 6), 1, 8), ((5, 4, 6), 2, 12), ((5, 4, 6), 0, 3), ((16, 8, 8, 4), 2, 8),
+                                          ((16, 8, 8, 4), 3, 4), ((128, 32, 32, 16), 0, 128), ((128, 32, 32, 16), 1, 32),
+                                          ((128, 32, 32, 16), 3, 16), ((48, 16), 1, 64), ((3, 130, 7), 1, 140), ((1, 1, 1), 1, 1)])
+def test_mode_dot_and_its_gradients(shape, mode, J):
+    from fidelityfusion_b200 import tensorly_compat as tl
+    gen = torch.Generator().manual_seed(sum(shape) + mode)
+    t = torch.randn(*shape, generator=gen).requires_grad_(True)
+    m = torch.randn(J, shape[mode], generator=gen).requires_grad_(True)
+    wgt = torch.randn(*(shape[:mode] + (J,) + shape[mode + 1:]), generator=gen)
+    ref = O.mode_dot(t, m, mode)
+    (ref * wgt).sum().backward()
+    tg = t.detach().to(DEV).requires_grad_(True)
+    mg = m.detach().to(DEV).requires_grad_(True)
+    out = tl.mode_dot(tg, mg, mode)
+    assert out.shape == ref.shape
+    assert rel_err(out.detach().cpu(), ref.detach()) < 1e-13
+    (out * wgt.to(DEV)).sum().backward()
+    assert rel_err(tg.grad.cpu(), t.grad) < 1e-12
+    assert rel_err(mg.grad.cpu(), m.grad) < 1e-12
+
+
+def test_mode_dot_vector_and_multi_mode():
+    from fidelityfusion_b200 import tensorly_compat as tl
+    gen = torch.Generator().manual_seed(3)
+    t = torch.randn(6, 5, 4, generator=gen)
+    v = torch.randn(5, generator=gen)
+    assert rel_err(tl.mode_dot(t.to(DEV), v.to(DEV), 1).cpu(), O.mode_dot(t, v, 1)) < 1e-13
+    mats = [torch.randn(3, 6, generator=gen), torch.randn(7, 5, generator=gen), torch.randn(2, 4, generator=gen)]
+    out = tl.multi_mode_dot(t.to(DEV), [m.to(DEV) for m in mats])
+    assert rel_err(out.cpu(), O.multi_mode_dot(t, mats)) < 1e-13
+    lam = [torch.rand(4, 1, generator=gen), torch.rand(3, 1, generator=gen)]
+    core = torch.ones(1, 1)
+    assert rel_err(tl.tucker_to_tensor((core.to(DEV), [l.to(DEV) for l in lam])).cpu(), O.kron_outer(lam)) < 1e-14
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 16, 33, 64, 128, 150])
+def test_eigh_jacobi(n):
+    from fidelityfusion_b200 import tensorly_compat as tl
+    gen = torch.Generator().manual_seed(n)
+    x = torch.rand(n, 3, generator=gen)
+    K = O.ard_kernel(x, x, torch.tensor([0.7, 1.1, 0.9]), torch.tensor([1.5]))     # PSD with tiny eigenvalues
+    w, V = tl.eigh(K.to(DEV))
+    w, V = w.cpu(), V.cpu()
+    wr = torch.linalg.eigvalsh(K)
+    scale = float(wr.abs().max())
+    assert float((w - wr).abs().max()) < 1e-13 * scale * max(n, 8)
+    assert bool((w[1:] >= w[:-1]).all())                                             # ascending like torch.linalg.eigh
+    assert float((V.T @ V - torch.eye(n)).abs().max()) < 1e-12
+    assert float((V @ torch.diag(w) @ V.T - K).abs().max()) < 1e-12 * scale * max(n, 8)
+
+
+def test_kat3_HOGP2023():
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    g = load_golden('kat3_HOGP2023')
+    h = HOGP({'fidelity_shapes': [torch.Size([3, 2])]}).double().to(DEV)
+    x, Y, xs = G(g['x']), G(g['Y']), G(g['xs'])
+    loss = h.compute_loss(x, Y)
+    assert abs(loss.item() - 1.193667663383912) < 1e-11
+    loss.backward()
+    assert rel_err(h.noise_box.value.grad.cpu(), g['g_noise_box_value']) < 1e-8
+    for k in range(3):
+        assert rel_err(h.kernel_list[k].length_scale.grad.cpu(), g[f'g_kernel_list_{k}_length_scale']) < 1e-7
+        assert rel_err(h.kernel_list[k].scale.grad.cpu(), g[f'g_kernel_list_{k}_scale']) < 1e-8
+    u, v = h.forward(xs)
+    assert rel_err(u.cpu(), g['u']) < 1e-9 and rel_err(v.cpu(), g['var']) < 1e-9
+    assert rel_err(h.A.cpu(), g['A']) < 1e-9
+
+
+def test_hogp2023_nondefault_params_and_y_gradient():
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    g = load_golden('hogp2023_params')
+    h = HOGP({'fidelity_shapes': [torch.Size([8, 8, 4])]}).double()
+    with torch.no_grad():
+        h.noise_box.value.fill_(3.0)
+        for i, k in enumerate(h.kernel_list):
+            k.length_scale.fill_(0.2 * (i + 1) - 0.3)
+            k.scale.fill_(0.1 * i)
+    h = h.to(DEV)
+    Y = G(g['Y']).requires_grad_(True)
+    loss = h.compute_loss(G(g['x']), Y)
+    assert abs(loss.item() - float(g['loss'])) <= 1e-9 * abs(float(g['loss']))
+    loss.backward()
+    assert rel_err(Y.grad.cpu(), g['gY']) < 1e-9
+    assert rel_err(h.A.cpu(), g['A']) < 1e-9 and rel_err(h.g.cpu(), g['g']) < 1e-8
+    assert rel_err(h.noise_box.value.grad.cpu(), g['g_noise_box_value']) < 1e-8
+    for k in range(4):
+        a, b = h.kernel_list[k].length_scale.grad.cpu(), g[f'g_kernel_list_{k}_length_scale']
+        assert abs(float(a) - float(b)) <= 1e-6 * max(abs(float(b)), 1e-3), (k, float(a), float(b))
+        a, b = h.kernel_list[k].scale.grad.cpu(), g[f'g_kernel_list_{k}_scale']
+        assert abs(float(a) - float(b)) <= 1e-6 * max(abs(float(b)), 1e-3), (k, float(a), float(b))
+    u, v = h.forward(G(g['xs']))
+    assert rel_err(u.cpu(), g['u']) < 1e-8 and rel_err(v.cpu(), g['var']) < 1e-8
+
+
+def test_c4_GAR2023_two_fidelity_loss_grads_predict():
+    """C4: gen-2023 GAR = HOGP on fidelity 0 + HOGP on the Matrix_Mapping residual (GAR_GeneralizedAutoAR.py:207-250)."""
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    from fidelityfusion_b200.MFGP_ver2023May.multiscale_coupling.matrix import Matrix_Mapping
+    g = load_golden('c4_GAR2023')
+    shape = torch.Size([8, 8, 4])
+    hs = torch.nn.ModuleList([HOGP({'fidelity_shapes': [shape]}), HOGP({'fidelity_shapes': [shape]})]).double().to(DEV)
+    mm = Matrix_Mapping({'low_fidelity_shape': shape, 'high_fidelity_shape': shape}).double().to(DEV)
+    x, Ylo, Yhi, xs = G(g['x']), G(g['Ylo']), G(g['Yhi']), G(g['xs'])
+    loss = hs[0].compute_loss(x, Ylo) + hs[1].compute_loss(x, mm.forward(Ylo, Yhi), update_data=True)
+    assert abs(loss.item() - float(g['loss'])) <= 1e-9 * abs(float(g['loss']))
+    loss.backward()
+    for k in range(3):
+        assert rel_err(mm.vectors[k].grad.cpu(), g[f'g_matrix_list_0_vectors_{k}']) < 1e-8
+    for f in range(2):
+        assert rel_err(hs[f].noise_box.value.grad.cpu(), g[f'g_hogp_list_{f}_noise_box_value']) < 1e-8
+        for k in range(4):
+            a = float(hs[f].kernel_list[k].scale.grad)
+            b = float(g[f'g_hogp_list_{f}_kernel_list_{k}_scale'])
+            assert abs(a - b) <= 1e-6 * max(abs(b), 1e-3), (f, k, a, b)
+            a = float(hs[f].kernel_list[k].length_scale.grad)
+            b = float(g[f'g_hogp_list_{f}_kernel_list_{k}_length_scale'])
+            assert abs(a - b) <= 1e-6 * max(abs(b), 1e-3), (f, k, a, b)
+    m0, v0 = hs[0].forward(xs)
+    m1, v1 = hs[1].forward(xs)
+    u, var = mm.backward(m0, m1), mm.var_backward(v0, v1)
+    assert rel_err(u.detach().cpu(), g['u']) < 1e-8 and rel_err(var.detach().cpu(), g['var']) < 1e-8
+
+
+@pytest.mark.parametrize('tag', ['gp', 'ffm'])
+def test_hogp_simple_copies(tag):
+    from fidelityfusion_b200.GaussianProcess.hogp_simple import HOGP_simple, HOGP_simple_ffm
+    from fidelityfusion_b200.GaussianProcess.kernel import SquaredExponentialKernel
+    g = load_golden(f'hogp_simple_{tag}')
+    cls = HOGP_simple if tag == 'gp' else HOGP_simple_ffm
+    k = SquaredExponentialKernel(0.2, 0.1)
+    hs = cls(k, 2.0, [8, 8, 4]).double().to(DEV)
+    x, Y, xs = G(g['x']), G(g['Y']), G(g['xs'])
+    loss = hs.log_likelihood(x, Y)
+    assert abs(loss.item() - float(g['loss'])) <= 1e-9 * abs(float(g['loss']))
+    loss.backward()
+    assert rel_err(hs.noise_variance.grad.cpu(), g['g_noise']) < 1e-8
+    assert rel_err(k.length_scale.grad.cpu(), g['g_length_scale']) < 1e-6      # reference differentiates through eigh
+    assert rel_err(k.signal_variance.grad.cpu(), g['g_signal_variance']) < 1e-6
+    u, v = hs.forward(x, xs)
+    assert rel_err(u.cpu(), g['u']) < 1e-8
+    # the 'ffm' copy inverts an un-jittered K0 (cond ~1e10): only a loose match is meaningful there
+    assert rel_err(v.cpu(), g['var']) < (1e-4 if tag == 'ffm' else 1e-8)
+
+
+def test_couplings_golden():
+    from fidelityfusion_b200.MFGP_ver2023May.multiscale_coupling.matrix import Matrix_Mapping
+    from fidelityfusion_b200.MFGP_ver2023May.multiscale_coupling.Residual import Residual
+    g = load_golden('couplings')
+    mm = Matrix_Mapping({'low_fidelity_shape': (4, 3), 'high_fidelity_shape': (8, 3), 'matrix_init_method': 'smooth',
+                         'rho_value_init': 0.8, 'trainable_rho': True}).double().to(DEV)
+    assert rel_err(mm.vectors[0].detach().cpu(), g['w0']) < 1e-12
+    lo, hi = G(g['lo']), G(g['hi'])
+    res = mm.forward(lo, hi)
+    assert rel_err(res.detach().cpu(), g['res']) < 1e-12
+    res.pow(2).sum().backward()
+    assert rel_err(mm.vectors[0].grad.cpu(), g['g_w0']) < 1e-11 and rel_err(mm.rho.grad.cpu(), g['g_rho']) < 1e-11
+    assert rel_err(mm.backward(lo, res.detach()).detach().cpu(), g['back']) < 1e-12
+    mm2 = Matrix_Mapping({'low_fidelity_shape': (4,), 'high_fidelity_shape': (8,), 'matrix_init_method': 'eye'})
+    assert rel_err(mm2.vectors[0].detach().double(), g['eye_init']) < 1e-7
+    r = Residual({'rho_value_init': 0.7}).double().to(DEV)
+    assert rel_err(r.forward(lo, lo * 2).detach().cpu(), g['resid_fwd']) < 1e-12
+    assert rel_err(r.backward(lo, lo * 2).detach().cpu(), g['resid_bwd']) < 1e-12
+
+
+def test_c4_full_size_kronecker_properties():
+    """BASELINE config 4 shape (N=128, 32x32x16): properties that need no CPU oracle at this size -
+    g = S^-1 y satisfies S g = y (S applied through mode products with the kernel matrices), and the loss
+    is invariant under the analytic-gradient check d/dtau by central differences."""
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    from fidelityfusion_b200 import tensorly_compat as tl
+    shape = torch.Size([32, 32, 16])
+    gen = torch.Generator().manual_seed(4)
+    x = torch.rand(128, 5, generator=gen).to(DEV)
+    Y = torch.randn(128, 32, 32, 16, generator=gen).to(DEV)
+    h = HOGP({'fidelity_shapes': [shape]}).double().to(DEV)
+    loss = h.compute_loss(x, Y)
+    loss.backward()
+    tau = 1.0 / h.noise_box.get().item()
+    Sg = tl.multi_mode_dot(h.g, [k.detach() for k in h.k_result_cache]) + tau * h.g
+    assert float((Sg - Y).abs().max()) < 1e-8 * float(Y.abs().max())
+    g0 = h.noise_box.value.grad.item()
+    eps = 1e-5
+    with torch.no_grad():
+        h.noise_box.value.add_(eps)
+        up = h.compute_loss(x, Y).item()
+        h.noise_box.value.sub_(2 * eps)
+        dn = h.compute_loss(x, Y).item()
+    assert abs((up - dn) / (2 * eps) - g0) <= 1e-6 * max(abs(g0), 1e-3)
