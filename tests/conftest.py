@@ -24,6 +24,16 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _default_dtype_f64():
+    """Harness convention of SURVEY.md 8(c): default dtype fp64 (tests that exercise fp32 switch explicitly)."""
+    import torch
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + '.npz')) as z:
         return {k: z[k] for k in z.files}

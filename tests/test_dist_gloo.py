@@ -61,4 +61,3 @@ def test_sharded_eval_two_ranks_gloo(Bn):
         for k, v in full.items():
             assert tuple(got[r][k].shape) == tuple(v.shape), k
             assert (got[r][k] == v.numpy()).all(), (r, k)                   # every rank holds the identical full result
-    torch.set_default_dtype(torch.float32)
