@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the GP hot path (BASELINE.json metric: "GP NLL+grad evals/sec (fp64, N=8192, d=16) & batched GPs/sec;
+% FP64 roofline").
+
+  python bench.py --gpus N --steps K --warmup W          # our CUDA path (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --steps K --warmup W  # the reference's CPU path (oracle port) on the host cores
+
+A step = ONE NLL+gradient evaluation of the single-fidelity ARD-RBF cigp of BASELINE config 2 (synthetic N=8192, d=16,
+D=1, fp64).  The large-N factorisation is not distributed (north_star): with N>1 GPUs every rank evaluates its own
+replica (e.g. a hyper-parameter restart) - "replicas only", weak scaling, no data-path collective.  The batched config
+(4096 independent GPs of N=512, d=8: BASELINE config 5) IS sharded across ranks with one all-gather and is reported in
+the `batched` object of the same JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_C2, D_C2 = 8192, 16
+F_ALG_C2 = N_C2 ** 3 + 4 * N_C2 ** 2 * D_C2 + 4 * N_C2 ** 2 * 1            # 5.543e11 FLOP / eval
+B_C5, N_C5, D_C5, NS_C5 = 4096, 512, 8, 64
+F_ALG_C5 = N_C5 ** 3 + 4 * N_C5 ** 2 * D_C5 + 4 * N_C5 ** 2 * 1            # 1.437e8 FLOP / GP
+
+
+def c2_inputs(torch):
+    """SURVEY.md 8(d) C2 recipe (seed 0)."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N_C2, D_C2, generator=g, dtype=torch.float64)
+    y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn(N_C2, 1, generator=g, dtype=torch.float64)
+    return x, y
+
+
+def c5_inputs(torch, lo, hi):
+    g = torch.Generator().manual_seed(5000)
+    x = torch.rand(B_C5, N_C5, D_C5, generator=g, dtype=torch.float64)
+    w = torch.randn(B_C5, D_C5, 1, generator=g, dtype=torch.float64)
+    y = torch.sin(3 * x @ w) + 0.05 * torch.randn(B_C5, N_C5, 1, generator=g, dtype=torch.float64)
+    ls = torch.exp(torch.rand(B_C5, D_C5, generator=g, dtype=torch.float64) * 2 - 1)
+    lb = torch.rand(B_C5, generator=g, dtype=torch.float64) * 3
+    xs = torch.rand(B_C5, NS_C5, D_C5, generator=g, dtype=torch.float64)
+    sl = slice(lo, hi)
+    return x[sl], y[sl], ls[sl], torch.ones(hi - lo, dtype=torch.float64), lb[sl], xs[sl]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples if len(s) > 3 + i)]
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+def cpu_eval_c2(torch, threads):
+    """One NLL+grad eval of C2 exactly as the reference performs it (oracle restatement: cdist kernel, torch.linalg.cholesky,
+    triangular solve, autograd backward) on the host cores."""
+    from oracle import ff_oracle as O
+    torch.set_num_threads(threads)
+    x, y = c2_inputs(torch)
+    ls, sv, lb = torch.ones(D_C2, dtype=torch.float64), torch.ones(1, dtype=torch.float64), torch.ones(1, dtype=torch.float64)
+    t0 = time.perf_counter()
+    loss, _ = O.cigp_ard_nll_and_grads(x, y, ls, sv, lb)
+    return time.perf_counter() - t0, loss
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port, all host threads)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    torch.set_default_dtype(torch.float64)
+    threads = os.cpu_count() or 1
+    budget = 240.0
+    t_start = time.perf_counter()
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, loss = cpu_eval_c2(torch, threads)
+        if i >= args.warmup:
+            times.append(dt)
+        elif i == 0 and dt * (args.warmup + args.steps) > budget:
+            # keep the whole run within a few minutes: drop the remaining warm-up evals (each eval is seconds long,
+            # far above any cold-start effect)
+            args.warmup = 1
+        if time.perf_counter() - t_start > budget and len(times) >= 1:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    val = 1e3 / ms
+    line = {
+        'impl': 'reference', 'metric': 'GP NLL+grad evals/sec (fp64, N=8192, d=16)', 'value': val, 'unit': 'evals/s',
+        'n_gpus': args.gpus, 'steps': len(times), 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'C2: single-fidelity ARD-RBF cigp NLL+grad, N=8192, d=16, D=1, fp64 (SURVEY 8d recipe, seed 0)'},
+        'cpu_baseline': {'value': val, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
+                         'sample': f'{len(times)} full NLL+grad evals of the C2 workload (N=8192) on the host, torch {torch.__version__} CPU/MKL'},
+        'e2e': {'value': val, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'nll': loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def measure_dgemm_peak(torch):
+    """FP64 roofline denominator: cuBLAS DGEMM 8192^3 through torch.matmul, best of 10 (MEASURED_PEAKS.json
+    has no fp64 entry)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    b = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2 * n ** 3 / best * 1e-9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--skip-batched', action='store_true')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 0)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the product path has no CPU fallback')
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    torch.set_default_dtype(torch.float64)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    from fidelityfusion_b200 import _lib
+    from fidelityfusion_b200.GaussianProcess.cigp_v10 import cigp
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
+    from fidelityfusion_b200.batched import batched_cigp_eval, shard_range, sharded_cigp_eval
+    lib = _lib.lib()                                    # fails loudly if the extension is missing
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak_tflops = measure_dgemm_peak(torch) if rank == 0 else 0.0
+
+    # ------------------------------------------------------------------ C2: one replica per rank
+    xh, yh = c2_inputs(torch)
+    xh, yh = xh.pin_memory(), yh.pin_memory()
+    model = cigp(ARDKernel(D_C2), 1.0).cuda()
+    model.factor_cache = None
+    xd, yd = xh.cuda(), yh.cuda()
+
+    def one_eval(x, y):
+        model.zero_grad(set_to_none=True)
+        loss = -model.negative_log_likelihood(x, y)      # the reference's training-step idiom, CIGAR.py:100-105
+        loss.backward()
+        return loss
+
+    for _ in range(args.warmup):
+        one_eval(xd, yd)
+    barrier()
+    launches0 = lib.ffgp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            loss = one_eval(xd, yd)
+        e1.record()
+        barrier()
+    launches = int(lib.ffgp_launch_count() - launches0)
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    nll_val = float(loss.item())
+    value = world * 1e3 / ms_step
+
+    # ------------------------------------------------------------------ e2e: host buffers in, scalars + gradients out
+    def one_eval_e2e():
+        x = xh.cuda(non_blocking=True)
+        y = yh.cuda(non_blocking=True)
+        l = one_eval(x, y)
+        out = torch.cat([l.reshape(1), model.kernel.length_scales.grad, model.kernel.signal_variance.grad, model.log_beta.grad])
+        return out.cpu()                                 # device -> host read of the step's result (sync)
+
+    for _ in range(2):
+        one_eval_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = one_eval_e2e()
+    barrier()
+    ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps)
+    e2e = {'value': world * 1e3 / ms_e2e, 'unit': 'evals/s', 'h2d_bytes_per_step': int(xh.numel() * 8 + yh.numel() * 8),
+           'd2h_bytes_per_step': int(res.numel() * 8), 'ms_per_step': ms_e2e}
+
+    # ------------------------------------------------------------------ batched C5, sharded across ranks
+    batched = None
+    if not args.skip_batched:
+        lo, hi = shard_range(B_C5, rank, world)
+        bx, by, bls, bsv, blb, bxs = [t.cuda() for t in c5_inputs(torch, 0, B_C5)]
+
+        def sweep():
+            return sharded_cigp_eval(bx, by, bls, bsv, blb, bxs)      # rank-local block [lo,hi) + ONE packed all-gather
+
+        for _ in range(3):
+            sweep()
+        barrier()
+        nsw = 5
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(nsw):
+            out = sweep()
+        b1.record()
+        barrier()
+        ms_sweep = max_over_ranks(b0.elapsed_time(b1) / nsw)
+        gps = B_C5 / ms_sweep * 1e3
+        batched = {'metric': 'batched GPs/sec (NLL+grad+predict, 4096 x N=512, d=8, N*=64)', 'value': gps, 'unit': 'GPs/s',
+                   'ms_per_sweep': ms_sweep, 'scaling': 'strong', 'per_rank_problems': hi - lo,
+                   'collective': 'none' if world == 1 else 'one all_gather_into_tensor of [B/R, 1+10+64+64] f64 per sweep',
+                   'tflops_alg': gps * F_ALG_C5 * 1e-12, 'nll_checksum': float(out['nll'].sum().item())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:
+        threads = os.cpu_count() or 1
+        dt, cpu_loss = cpu_eval_c2(torch, threads)
+        cpu = {'value': 1.0 / dt, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
+               'sample': '1 full NLL+grad eval of the C2 workload (N=8192, d=16) with the oracle port of the reference '
+                         f'(torch {torch.__version__} CPU); nll={cpu_loss:.10f}',
+               'gpu_vs_cpu_nll_rel_diff': abs(cpu_loss - nll_val) / abs(cpu_loss)}
+
+    achieved = F_ALG_C2 * (world * 1e3 / ms_step) * 1e-12 / world      # per-GPU TFLOP/s on algorithmic FLOPs
+    line = {
+        'metric': 'GP NLL+grad evals/sec (fp64, N=8192, d=16)', 'value': value, 'unit': 'evals/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'C2: single-fidelity ARD-RBF cigp NLL+grad, N=8192, d=16, D=1, fp64 (SURVEY 8d recipe, seed 0)',
+                   'parallelism': 'replicas only (one independent eval per GPU; a single large-N Cholesky is not distributed)',
+                   'l2': 'working set 1.6 GB per eval >> 126 MB L2 (no flush needed)', 'nll': nll_val},
+        'e2e': e2e,
+        'gpu_launches': launches,
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': None,
+                     'note': 'FP64 tensor pipe (DMMA). achieved = F_alg (N^3 + 4N^2 d + 4N^2 D = 5.543e11 FLOP/eval, SURVEY 8d) / '
+                             'CUDA-event time of the whole eval (all launches; the DMMA GEMM kernel is >90% of it). '
+                             'peak = torch.matmul fp64 8192^3 best of 10 measured live in this run (MEASURED_PEAKS.json has '
+                             'no fp64 entry); DMMA issue-bound peak measured at 37.1 TFLOP/s (profiles/r01_fp64_peak_microbench.txt)'},
+        'clocks': clk.summary(),
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    if batched is not None:
+        batched['roofline_frac'] = batched['tflops_alg'] / world / peak_tflops if peak_tflops else None
+        line['batched'] = batched
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -28,7 +28,7 @@ class _CholPieces(torch.autograd.Function):
         L = B.lib()
         n, D = y.shape
         dev = y.device
-        want = (y.requires_grad or cov.requires_grad) and torch.is_grad_enabled()
+        want = any(ctx.needs_input_grad)
         yc, cc = ops._f64c(y).unsqueeze(0), ops._f64c(cov).unsqueeze(0)
         core = torch.empty(1, dtype=torch.float64, device=dev)
         logdet = torch.empty(1, dtype=torch.float64, device=dev)

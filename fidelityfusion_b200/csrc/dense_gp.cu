@@ -11,6 +11,7 @@
 namespace ffgp {
 
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;   // kernels launched by this library (bench.py reports it as gpu_launches)
 int fail(int code, const char* fmt, const char* a = "") {
   snprintf(g_err, sizeof(g_err), fmt, a);
   return code;
@@ -19,6 +20,12 @@ int fail(int code, const char* fmt, const char* a = "") {
   do {                                                                 \
     cudaError_t e__ = (x);                                             \
     if (e__ != cudaSuccess) return fail(-100, "CUDA error: %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+#define FFGP_LAUNCHED()          \
+  do {                           \
+    ++ffgp::g_launches;          \
+    FFGP_CUDA(cudaGetLastError()); \
   } while (0)
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -45,6 +52,7 @@ static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = sA; p.sB = sB; p.sC = sC; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only; p.kmode = kmode;
   p.heavy_first = 1;
+  ++g_launches;
   bool big = (M % 128 == 0) && (N % 128 == 0);
   if (big) {
     const long long tm = M / 128, tn = N / 128;
@@ -155,6 +163,7 @@ static cudaError_t factor_rec(const FactorCtx& c, int off, int n) {
   if (n == BASE_N) {
     potrf_trtri_base_kernel<<<c.batch, 256, BASE_SMEM, c.st>>>(c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part,
                                                                c.nblk, off / BASE_N, c.info, off);
+    ++g_launches;
     return cudaGetLastError();
   }
   // split at a multiple of 128: top half gets the larger power-of-two-ish share
@@ -218,7 +227,7 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   kp.sK = (long long)w.np * w.np;
   kp.symmetric = 1; kp.lower_only = 1; kp.clamp = a.clamp;
   kernel_matrix_kernel<<<dim3(w.np / 64, w.np / 64, nb), 256, 0, st>>>(kp);
-  FFGP_CUDA(cudaGetLastError());
+  FFGP_LAUNCHED();
   FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};
   FFGP_CUDA(factor_rec(c, 0, w.np));
   return 0;
@@ -232,19 +241,19 @@ static int solve_rhs(const DenseArgs& a, const DenseWs& w, int b0, int nb, cudaS
     const long long sG = (long long)w.np * a.D;
     trmv_lower_kernel<8><<<dim3(w.np / 8, nb), 256, 0, st>>>(w.M, w.np, sM, y, a.n, a.D, (long long)a.n * a.D, w.Gm, sG,
                                                              w.rowsq, w.np);
-    FFGP_CUDA(cudaGetLastError());
+    FFGP_LAUNCHED();
     colsum_weighted_kernel<8><<<dim3(w.np / 32, nb), 256, 0, st>>>(w.M, w.np, sM, w.np, w.Gm, a.D, sG, a.D, w.alpha, a.D,
                                                                    sG, w.np, 1, 0);
-    FFGP_CUDA(cudaGetLastError());
+    FFGP_LAUNCHED();
   } else {
     const long long sG = (long long)w.np * w.Dp;
     dim3 blk(32, 8), grd((w.Dp + 31) / 32, (w.np + 7) / 8, nb);
     pad_copy_kernel<<<grd, blk, 0, st>>>(y, a.n, a.D, a.D, (long long)a.n * a.D, w.Ypad, w.np, w.Dp, w.Dp, sG);
-    FFGP_CUDA(cudaGetLastError());
+    FFGP_LAUNCHED();
     FFGP_CUDA(gemm(true, false, w.M, w.np, sM, w.Ypad, w.Dp, sG, w.Gm, w.Dp, sG, w.np, w.Dp, w.np, 1.0, 0.0, 0, K_LE_ROW,
                    nb, st));
     rowsq_kernel<<<dim3(w.np / 8, nb), 256, 0, st>>>(w.Gm, w.Dp, sG, w.Dp, w.rowsq, w.np);
-    FFGP_CUDA(cudaGetLastError());
+    FFGP_LAUNCHED();
     FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.Gm, w.Dp, sG, w.alpha, w.Dp, sG, w.np, w.Dp, w.np, 1.0, 0.0, 0,
                    K_GE_ROW, nb, st));
   }
@@ -257,7 +266,7 @@ static int copy_alpha_out(const DenseArgs& a, const DenseWs& w, int b0, int nb, 
   dim3 blk(32, 8), grd((a.D + 31) / 32, (a.n + 7) / 8, nb);
   pad_copy_kernel<<<grd, blk, 0, st>>>(w.alpha, w.np, Dw, Dw, (long long)w.np * Dw,
                                        out_alpha + (long long)b0 * a.n * a.D, a.n, a.D, a.D, (long long)a.n * a.D);
-  FFGP_CUDA(cudaGetLastError());
+  FFGP_LAUNCHED();
   return 0;
 }
 
@@ -268,7 +277,21 @@ using namespace ffgp;
 extern "C" {
 
 int ffgp_version(void) { return FFGP_VERSION; }
+unsigned long long ffgp_launch_count(void) { return g_launches; }
 const char* ffgp_last_error_string(void) { return g_err; }
+
+int ffgp_gemm_f64(int a_kmajor, int b_kmajor, const double* A, int lda, long long strideA, const double* B, int ldb,
+                  long long strideB, double* C, int ldc, long long strideC, int M, int N, int K, double alpha, double beta,
+                  int lower_only, int kmode, int batch, void* stream) {
+  if (!A || !B || !C) return fail(-1, "ffgp_gemm_f64: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0 || M % 64 || N % 64 || K % 16) return fail(-2, "ffgp_gemm_f64: M,N %% 64 and K %% 16 required");
+  if (lower_only && M != N) return fail(-2, "ffgp_gemm_f64: lower_only needs M == N");
+  if (kmode < 0 || kmode > 4) return fail(-2, "ffgp_gemm_f64: bad kmode");
+  if ((lda | ldb | ldc) & 1) return fail(-2, "ffgp_gemm_f64: leading dimensions must be even (16-byte rows)");
+  FFGP_CUDA(gemm(a_kmajor != 0, b_kmajor != 0, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, M, N, K, alpha, beta,
+                 lower_only, kmode, batch, (cudaStream_t)stream));
+  return 0;
+}
 
 size_t ffgp_dense_workspace_bytes(int n, int d, int D, int ns, int batch) {
   if (n <= 0 || D <= 0 || batch <= 0 || d < 0) return 0;
@@ -288,7 +311,7 @@ int ffgp_kernel_matrix_f64(const double* x1, const double* x2, const double* inv
   kp.np1 = round_up(n1, 64); kp.np2 = round_up(n2, 64); kp.ldk = n2; kp.sK = (long long)n1 * n2;
   kp.symmetric = 0; kp.lower_only = 0; kp.clamp = clamp; kp.bounded = 1;
   kernel_matrix_kernel<<<dim3(kp.np2 / 64, kp.np1 / 64, batch), 256, 0, st>>>(kp);
-  FFGP_CUDA(cudaGetLastError());
+  FFGP_LAUNCHED();
   return 0;
 }
 
@@ -317,7 +340,7 @@ int ffgp_dense_nll_f64(const double* x, const double* y, const double* inv_ls, c
     if ((rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
     nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, D, out_nll + b0,
                                           out_logdet ? out_logdet + b0 : nullptr);
-    FFGP_CUDA(cudaGetLastError());
+    FFGP_LAUNCHED();
     if ((rc = copy_alpha_out(a, w, b0, nb, out_alpha, st)) != 0) return rc;
     if (!want_grad) continue;
     // S = M^T M (lower) into the dead A buffer
@@ -342,11 +365,11 @@ int ffgp_dense_nll_f64(const double* x, const double* y, const double* inv_ls, c
     gp.G_out = g_sigma ? g_sigma + (long long)b0 * n * n : nullptr; gp.sGo = (long long)n * n;
     gp.have_k = amp ? 1 : 0;
     grad_contract_kernel<<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
-    FFGP_CUDA(cudaGetLastError());
+    FFGP_LAUNCHED();
     if (amp) {
       grad_finish_kernel<<<nb, 128, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,
                                              g_inv_ls + (long long)b0 * d, g_amp + b0);
-      FFGP_CUDA(cudaGetLastError());
+      FFGP_LAUNCHED();
     }
   }
   return 0;
@@ -392,14 +415,14 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, c
       kp.sigma_add = Ks + (long long)b0 * n * ns; kp.ssig = (long long)n * ns;
     }
     kernel_matrix_kernel<<<dim3(w.nsp / 64, w.np / 64, nb), 256, 0, st>>>(kp);
-    FFGP_CUDA(cudaGetLastError());
+    FFGP_LAUNCHED();
     // mean = Kx^T alpha
     if (!w.gemm_rhs) {
       colsum_weighted_kernel<8><<<dim3(w.nsp / 32, nb), 256, 0, st>>>(w.Kx, w.nsp, sKx, w.np, w.alpha, D,
                                                                       (long long)w.np * D, D,
                                                                       out_mean + (long long)b0 * ns * D, D,
                                                                       (long long)ns * D, ns, 0, 0);
-      FFGP_CUDA(cudaGetLastError());
+      FFGP_LAUNCHED();
     } else {
       const long long sG = (long long)w.np * w.Dp, sMp = (long long)w.nsp * w.Dp;
       FFGP_CUDA(gemm(false, false, w.Kx, w.nsp, sKx, w.alpha, w.Dp, sG, w.meanp, w.Dp, sMp, w.nsp, w.Dp, w.np, 1.0, 0.0, 0,
@@ -407,7 +430,7 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, c
       dim3 blk(32, 8), grd((D + 31) / 32, (ns + 7) / 8, nb);
       pad_copy_kernel<<<grd, blk, 0, st>>>(w.meanp, w.nsp, w.Dp, w.Dp, sMp, out_mean + (long long)b0 * ns * D, ns, D, D,
                                            (long long)ns * D);
-      FFGP_CUDA(cudaGetLastError());
+      FFGP_LAUNCHED();
     }
     if (!out_cov) continue;
     // V = M Kx
@@ -426,23 +449,23 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, c
       }
       kq.offset = cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr; kq.soff = params_batched ? 1 : 0;
       kernel_matrix_kernel<<<dim3(w.nsp / 64, w.nsp / 64, nb), 256, 0, st>>>(kq);
-      FFGP_CUDA(cudaGetLastError());
+      FFGP_LAUNCHED();
       // cov = Kxx - V^T V
       FFGP_CUDA(gemm(false, false, w.V, w.nsp, sKx, w.V, w.nsp, sKx, w.Kxx, w.nsp, sKxx, w.nsp, w.nsp, w.np, -1.0, 1.0, 0,
                      K_FULL, nb, st));
       dim3 blk(32, 8), grd((ns + 31) / 32, (ns + 7) / 8, nb);
       unpad_copy_kernel<<<grd, blk, 0, st>>>(w.Kxx, w.nsp, sKxx, out_cov + (long long)b0 * ns * ns, ns, ns,
-                                             (long long)ns * ns);
-      FFGP_CUDA(cudaGetLastError());
+                                             (long long)ns * ns, 0);
+      FFGP_LAUNCHED();
     } else {
       colsum_weighted_kernel<1><<<dim3(w.nsp / 32, nb), 256, 0, st>>>(w.V, w.nsp, sKx, w.np, nullptr, 0, 0, 1, w.colsq, 1,
                                                                       w.nsp, w.nsp, 0, 1);
-      FFGP_CUDA(cudaGetLastError());
+      FFGP_LAUNCHED();
       var_diag_kernel<<<dim3((ns + 127) / 128, nb), 128, 0, st>>>(w.colsq, amp + (params_batched ? b0 : 0),
                                                                   params_batched ? 1 : 0,
                                                                   cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr,
                                                                   params_batched ? 1 : 0, out_cov + (long long)b0 * ns, ns);
-      FFGP_CUDA(cudaGetLastError());
+      FFGP_LAUNCHED();
     }
   }
   return 0;
@@ -464,18 +487,18 @@ int ffgp_potrf_trtri_f64(const double* A, int n, int batch, void* workspace, siz
     if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
     dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8, nb);
     if (L) {
-      unpad_copy_kernel<<<grd, blk, 0, st>>>(w.L, w.np, (long long)w.np * w.np, L + (long long)b0 * n * n, n, n, (long long)n * n);
-      FFGP_CUDA(cudaGetLastError());
+      unpad_copy_kernel<<<grd, blk, 0, st>>>(w.L, w.np, (long long)w.np * w.np, L + (long long)b0 * n * n, n, n, (long long)n * n, 1);
+      FFGP_LAUNCHED();
     }
     if (Linv) {
-      unpad_copy_kernel<<<grd, blk, 0, st>>>(w.M, w.np, (long long)w.np * w.np, Linv + (long long)b0 * n * n, n, n, (long long)n * n);
-      FFGP_CUDA(cudaGetLastError());
+      unpad_copy_kernel<<<grd, blk, 0, st>>>(w.M, w.np, (long long)w.np * w.np, Linv + (long long)b0 * n * n, n, n, (long long)n * n, 1);
+      FFGP_LAUNCHED();
     }
     if (logdet) {
       // rowsq is unused here: zero it so the reducer returns logdet only
       FFGP_CUDA(cudaMemsetAsync(w.rowsq, 0, sizeof(double) * (size_t)nb * w.np, st));
       nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, 1, nullptr, logdet + b0);
-      FFGP_CUDA(cudaGetLastError());
+      FFGP_LAUNCHED();
     }
   }
   return 0;

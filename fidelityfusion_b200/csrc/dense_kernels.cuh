@@ -492,15 +492,15 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
         }
         if (gi == gj) {
           if (p.g_diag) p.g_diag[b * p.sgd + gi] = G;
-          wgt = G * amp;                       // K_ii = amp, dz = 0
+          wgt = G;                             // K_ii / amp = 1, dz = 0
         } else if (p.have_k) {
           double sq = 0.0;
           for (int k = 0; k < d; k++) { const double dz = xi[r * ldx + k] - xj[c * ldx + k]; sq = fma(dz, dz, sq); }
-          wgt = 2.0 * G * amp * exp(-0.5 * sq);   // (i,j) and (j,i)
+          wgt = 2.0 * G * exp(-0.5 * sq);      // (i,j) and (j,i); amplitude applied below
         }
       }
-      Wv[a][q] = wgt;
-      sumW += wgt;
+      sumW += wgt;                             // sum G o (K / amp): d/d amp needs no division (amp may be 0)
+      Wv[a][q] = wgt * amp;
     }
   }
   const int warp = tid >> 5, lane = tid & 31;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
   }
 }
 
-// g_w[k] = -(1/w_k) sum_t partial[t][k];  g_amp = (1/amp) sum_t partial[t][d]
+// g_w[k] = -(1/w_k) sum_t partial[t][k];  g_amp = sum_t partial[t][d]  (partials of G o K/amp)
 __global__ void __launch_bounds__(128) grad_finish_kernel(const double* __restrict__ partial, int npart, int d,
                                                           const double* __restrict__ w, long long sw,
                                                           const double* __restrict__ amp, long long samp,
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(128) grad_finish_kernel(const double* __restri
     const double* pp = partial + (long long)b * npart * (d + 1) + k;
     for (int t = 0; t < npart; t++) s += pp[(long long)t * (d + 1)];
     if (k < d) g_w[(long long)b * d + k] = -s / w[b * sw + k];
-    else g_amp[b] = s / amp[b * samp];
+    else g_amp[b] = s;
   }
 }
 
@@ -580,11 +580,11 @@ __global__ void pad_copy_kernel(const double* __restrict__ src, int rows_src, in
 // dst[i][j] = a * src[i][j] + add[b]   (cov = Kxx - V^T V + noise offset is produced by the GEMM epilogue;
 // this kernel only copies the padded result into the user's [ns][ns] array)
 __global__ void unpad_copy_kernel(const double* __restrict__ src, int lds, long long ssrc,
-                                  double* __restrict__ dst, int rows, int cols, long long sdst) {
+                                  double* __restrict__ dst, int rows, int cols, long long sdst, int lower_only) {
   const int b = blockIdx.z;
   const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
   if (r >= rows || c >= cols) return;
-  dst[b * sdst + (long long)r * cols + c] = src[b * ssrc + (long long)r * lds + c];
+  dst[b * sdst + (long long)r * cols + c] = (lower_only && c > r) ? 0.0 : src[b * ssrc + (long long)r * lds + c];
 }
 
 // var[s] = kss_amp + offset - colsq[s]   (diagonal predictive variance; K(x*,x*)_ss = amp)

@@ -17,6 +17,7 @@
 
 namespace ffgp {
 int fail(int code, const char* fmt, const char* a);
+extern unsigned long long g_launches;
 
 #define FFGP_CUDA(x)                                                   \
   do {                                                                 \
@@ -392,10 +393,10 @@ __global__ void __launch_bounds__(256) kernel_bwd_kernel(const double* __restric
       if (gi < n1 && gj < n2) {
         double sq = 0.0;
         for (int k = 0; k < d; k++) { const double dz = xi[r * ldx + k] - xj[c * ldx + k]; sq = fma(dz, dz, sq); }
-        wgt = gK[(long long)gi * n2 + gj] * a * exp(-0.5 * sq);
+        wgt = gK[(long long)gi * n2 + gj] * exp(-0.5 * sq);
       }
-      Wv[u][v] = wgt;
       sumW += wgt;
+      Wv[u][v] = wgt * a;
     }
   const int warp = tid >> 5, lane = tid & 31;
   for (int k = 0; k < d; k++) {
@@ -432,7 +433,7 @@ __global__ void kernel_bwd_finish_kernel(const double* __restrict__ partial, int
     double s = 0.0;
     for (int t = 0; t < npart; t++) s += partial[(long long)t * (d + 1) + k];
     if (k < d) g_w[k] = -s / w[k];
-    else g_amp[0] = s / amp[0];
+    else g_amp[0] = s;
   }
 }
 
@@ -459,6 +460,7 @@ int ffgp_mode_dot_f64(const double* t, const double* mat, double* out, long long
   const long long nchunks = (ncols + MD_COLS - 1) / MD_COLS;
   const int gx = (int)std::min<long long>(nchunks, 148LL * 8);
   mode_dot_kernel<<<dim3(gx, (J + 127) / 128), 256, 0, (cudaStream_t)stream>>>(t, mat, out, ncols, I, inner, J, transpose_mat);
+  ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -486,9 +488,11 @@ int ffgp_mode_gram_f64(const double* X, const double* Y, double* G, long long ou
   cudaStream_t st = (cudaStream_t)stream;
   mode_gram_kernel<<<dim3((Jb + MG_T - 1) / MG_T, (Ja + MG_T - 1) / MG_T, ns), 256, 0, st>>>(X, Y, (double*)scratch, ncols, inner,
                                                                                              Ja, Jb, cps);
+  ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   const long long nelem = (long long)Ja * Jb;
   gram_reduce_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>((const double*)scratch, ns, nelem, G);
+  ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -510,8 +514,10 @@ int ffgp_kron_core_f64(const double* T1, const double* lambdas, const int* sizes
   const int nb = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
   cudaStream_t st = (cudaStream_t)stream;
   kron_core_kernel<<<nb, 256, 0, st>>>(T1, lambdas, s, noise_inv, add_scalar, total, out_core, out_A, (double*)scratch);
+  ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   kron_sums_finish_kernel<<<1, 32, 0, st>>>((const double*)scratch, nb, out_sums);
+  ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -525,6 +531,7 @@ int ffgp_kron_scale_f64(const double* in, const double* lambdas, const int* size
   for (int m = 0; m < nmodes; m++) total *= sizes_host[m];
   const int nb = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
   kron_scale_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(in, lambdas, s, skip_mode, divide_by_A, noise_inv, add_scalar, total, out);
+  ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -553,6 +560,7 @@ int ffgp_syevj_f64(const double* A, int n, int batch, double* w, double* V, void
   double* wa = in_smem ? nullptr : vt + (size_t)batch * n * n;
   FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
   syevj_kernel<<<batch, SYEVJ_THREADS, smem, st>>>(A, n, w, V, wa, vt, info, 40);
+  ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -583,9 +591,11 @@ int ffgp_kernel_matrix_bwd_f64(const double* x1, const double* x2, const double*
     const double* av = amp + (params_batched ? b : 0);
     kernel_bwd_kernel<<<dim3(gx, gy), 256, smem, st>>>(x1 + (size_t)b * n1 * d, x2 + (size_t)b * n2 * d, wv, av,
                                                        gK + (size_t)b * n1 * n2, n1, n2, d, part);
-    FFGP_CUDA(cudaGetLastError());
+    ++ffgp::g_launches;
+  FFGP_CUDA(cudaGetLastError());
     kernel_bwd_finish_kernel<<<1, 128, 0, st>>>(part, gx * gy, d, wv, av, g_inv_ls + (size_t)b * d, g_amp + b);
-    FFGP_CUDA(cudaGetLastError());
+    ++ffgp::g_launches;
+  FFGP_CUDA(cudaGetLastError());
   }
   return 0;
 }

@@ -96,8 +96,9 @@ class _DenseNLL(torch.autograd.Function):
         x_, y_, il_, amp_, dg_, sg_, n, d, D, batch, pb, squeeze = _norm_batch(x, y, inv_ls, amp, diag_add, sigma_add)
         dev = y.device
         L = B.lib()
-        need = [t is not None and t.requires_grad for t in (y, inv_ls, amp, diag_add, sigma_add)]
-        want_grad = any(need) and torch.is_grad_enabled()
+        # (grad mode is off inside Function.forward: ask autograd which inputs need a gradient instead)
+        need = list(ctx.needs_input_grad[1:6])            # y, inv_ls, amp, diag_add, sigma_add
+        want_grad = any(need)
         xc = _f64c(x_) if x_ is not None else None
         yc = _f64c(y_)
         ilc = _f64c(il_) if il_ is not None else None

@@ -28,6 +28,21 @@ extern "C" {
 
 int ffgp_version(void);
 const char* ffgp_last_error_string(void);  /* host string, thread-local */
+unsigned long long ffgp_launch_count(void); /* kernels launched by the library so far (host counter) */
+
+/* ---------------------------------------------------------------------------------------
+ * The level-3 building block of the whole dense path, exported for unit tests and profiling:
+ *   C = alpha * op(A) * op(B) + beta * C   on the FP64 tensor pipe (DMMA), row-major, `batch` strided problems.
+ *   a_kmajor: A(i,p) = A[i*lda+p] else A[p*lda+i];   b_kmajor: B(p,j) = B[j*ldb+p] else B[p*ldb+j]
+ *   lower_only: only tiles on/below the diagonal are produced (M == N);
+ *   kmode: 0 full K; 1 p < i0+T (A lower-tri rows); 2 p < j0+T (B[j][p] lower-tri); 3 p >= j0 (B[p][j] lower-tri);
+ *          4 p >= i0 (A[p][i] lower-tri) - the K range of a tile shrinks, no special kernel.
+ * M, N must be multiples of 64 and K of 16 (the library pads its own problems to 128).
+ * Replaces torch.triangular_solve / cholesky_solve / mm / LinalgCholeskyExBackward0's GEMMs.
+ * --------------------------------------------------------------------------------------- */
+int ffgp_gemm_f64(int a_kmajor, int b_kmajor, const double* A, int lda, long long strideA,
+                  const double* B, int ldb, long long strideB, double* C, int ldc, long long strideC,
+                  int M, int N, int K, double alpha, double beta, int lower_only, int kmode, int batch, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Stationary squared-exponential family, one parameterisation for the reference's three:

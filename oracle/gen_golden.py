@@ -285,7 +285,7 @@ def gen_c4():
         h.noise_box.value.fill_(3.0)
         for i, k in enumerate(h.kernel_list):
             k.length_scale.fill_(0.2 * (i + 1) - 0.3)
-            k.scale.fill_(0.1 * i)
+            k.scale.fill_(0.1 * (i + 1))
     Y = Yhi.clone().requires_grad_(True)
     loss = h.compute_loss(x, Y)
     loss.backward()

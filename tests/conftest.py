@@ -41,8 +41,11 @@ def load_golden(name):
 
 def rel_err(a, b):
     """norm-wise relative error |a-b|_inf / max(|b|_inf, tiny)."""
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    def arr(v):
+        if hasattr(v, 'detach'):
+            v = v.detach().cpu().numpy()
+        return np.asarray(v, dtype=np.float64)
+    a, b = arr(a), arr(b)
     assert a.shape == b.shape, (a.shape, b.shape)
     denom = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
     return float(np.max(np.abs(a - b))) / denom if b.size else 0.0

@@ -103,7 +103,7 @@ def test_hogp2023_nondefault_params_and_y_gradient():
         h.noise_box.value.fill_(3.0)
         for i, k in enumerate(h.kernel_list):
             k.length_scale.fill_(0.2 * (i + 1) - 0.3)
-            k.scale.fill_(0.1 * i)
+            k.scale.fill_(0.1 * (i + 1))
     h = h.to(DEV)
     Y = G(g['Y']).requires_grad_(True)
     loss = h.compute_loss(G(g['x']), Y)

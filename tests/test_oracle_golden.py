@@ -97,7 +97,7 @@ def test_kat3_HOGP2023():
 
 def test_hogp2023_params_and_ygrad():
     g = load_golden('hogp2023_params')
-    params = [(0.2 * (i + 1) - 0.3, 0.1 * i) for i in range(4)]
+    params = [(0.2 * (i + 1) - 0.3, 0.1 * (i + 1)) for i in range(4)]
     x, Y, xs, ps, Ks = _hogp_from_golden(g, 3, params)
     Y = Y.clone().requires_grad_(True)
     nv = P(3.0)
