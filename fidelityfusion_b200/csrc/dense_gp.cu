@@ -464,7 +464,7 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, c
       var_diag_kernel<<<dim3((ns + 127) / 128, nb), 128, 0, st>>>(w.colsq, amp + (params_batched ? b0 : 0),
                                                                   params_batched ? 1 : 0,
                                                                   cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr,
-                                                                  params_batched ? 1 : 0, out_cov + (long long)b0 * ns, ns);
+                                                                  params_batched ? 1 : 0, out_cov + (long long)b0 * ns, ns, w.nsp);
       FFGP_LAUNCHED();
     }
   }

@@ -589,10 +589,11 @@ __global__ void unpad_copy_kernel(const double* __restrict__ src, int lds, long 
 
 // var[s] = kss_amp + offset - colsq[s]   (diagonal predictive variance; K(x*,x*)_ss = amp)
 __global__ void var_diag_kernel(const double* __restrict__ colsq, const double* __restrict__ amp, long long samp,
-                                const double* __restrict__ offset, long long soff, double* __restrict__ var, int ns) {
+                                const double* __restrict__ offset, long long soff, double* __restrict__ var, int ns,
+                                int ld_colsq) {
   const int b = blockIdx.y, s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ns) return;
-  var[(long long)b * ns + s] = amp[b * samp] + (offset ? offset[b * soff] : 0.0) - colsq[(long long)b * ns + s];
+  var[(long long)b * ns + s] = amp[b * samp] + (offset ? offset[b * soff] : 0.0) - colsq[(long long)b * ld_colsq + s];
 }
 
 }  // namespace ffgp
