@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "../../include/ffgp.h"
 #include "dense_kernels.cuh"
@@ -47,11 +48,14 @@ static int num_sms() {
 
 static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long long sA, const double* B, int ldb,
                         long long sB, double* C, int ldc, long long sC, int M, int N, int K, double alpha, double beta,
-                        int lower_only, int kmode, int batch, cudaStream_t st) {
+                        int lower_only, int kmode, int batch, cudaStream_t st, int inner = 1, long long iA = 0,
+                        long long iB = 0, long long iC = 0) {
   GemmParams p;
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = sA; p.sB = sB; p.sC = sC; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only; p.kmode = kmode;
   p.heavy_first = 1;
+  p.inner = inner; p.iA = iA; p.iB = iB; p.iC = iC;
+  batch *= inner;
   ++g_launches;
   bool big = (M % 128 == 0) && (N % 128 == 0);
   if (big) {
@@ -188,6 +192,133 @@ static cudaError_t factor_rec(const FactorCtx& c, int off, int n) {
   return cudaSuccess;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Production schedule (profiles/r01_launches_c2_v1.csv showed the fully recursive form spending 23 % of an
+// evaluation in 64 serialised 128-block kernels and 17 % in 242 small GEMM launches):
+//   1. right-looking blocked Cholesky with outer block NB: the diagonal block is factored (and inverted) by
+//      factor_rec on a high-priority side stream ONE STEP AHEAD of the trailing update (look-ahead): as soon as the
+//      next block column has received its rank-NB update, its diagonal block + TRSM run concurrently with the rest
+//      of the SYRK, so the serial panel work leaves the critical path while the trailing matrix is large;
+//   2. triangular inverse bottom-up: with the diagonal-block inverses known, M21 = -M22 L21 M11 of ALL nodes of one
+//      tree level is a single batched launch pair (inner batch level of the GEMM), 2 launches per level;
+//   3. (gradient) S = M^T M, one launch.
+// ---------------------------------------------------------------------------------------------
+struct AuxStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+};
+static AuxStream g_aux[64];
+
+static cudaError_t get_aux(AuxStream** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  AuxStream& a = g_aux[dev & 63];
+  if (!a.st) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&a.st, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&a.ev_main, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&a.ev_aux, cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  *out = &a;
+  return cudaSuccess;
+}
+
+static int g_outer_nb = 256;     // outer block of the right-looking sweep (128 or 256); FFGP_NB overrides
+static int outer_nb() {
+  static bool init = false;
+  if (!init) {
+    const char* e = getenv("FFGP_NB");
+    if (e) { int v = atoi(e); if (v == 128 || v == 256 || v == 512) g_outer_nb = v; }
+    init = true;
+  }
+  return g_outer_nb;
+}
+
+static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahead) {
+  cudaError_t e;
+  int NB = outer_nb();
+  if (np % NB != 0) NB = BASE_N;
+  const int nblk = np / NB;
+  AuxStream* aux = nullptr;
+  if (lookahead && nblk > 2) {
+    if ((e = get_aux(&aux)) != cudaSuccess) return e;
+  }
+  FactorCtx ca = c;                 // context of the panel (side) stream
+  if (aux) ca.st = aux->st;
+  auto at = [&](int bi, int bj) { return (long long)bi * NB * c.ld + (long long)bj * NB; };
+  // block column 0
+  if ((e = factor_rec(c, 0, NB)) != cudaSuccess) return e;
+  if (nblk > 1) {
+    if ((e = gemm(true, true, c.A + at(1, 0), c.ld, c.sb, c.M + at(0, 0), c.ld, c.sb, c.L + at(1, 0), c.ld, c.sb,
+                  np - NB, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, c.st)) != cudaSuccess) return e;
+  }
+  for (int k = 0; k + 1 < nblk; k++) {
+    const int rows1 = np - (k + 1) * NB;            // rows below block row k
+    // (a) rank-NB update of block column k+1
+    if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1), c.ld,
+                  c.sb, rows1, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+    cudaStream_t ps = c.st;
+    if (aux) {
+      if ((e = cudaEventRecord(aux->ev_main, c.st)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(aux->st, aux->ev_main, 0)) != cudaSuccess) return e;
+      ps = aux->st;
+    }
+    // (b) panel k+1: diagonal block (factor + inverse), then TRSM of the rows below it
+    if ((e = factor_rec(aux ? ca : c, (k + 1) * NB, NB)) != cudaSuccess) return e;
+    const int rows2 = np - (k + 2) * NB;
+    if (rows2 > 0) {
+      if ((e = gemm(true, true, c.A + at(k + 2, k + 1), c.ld, c.sb, c.M + at(k + 1, k + 1), c.ld, c.sb,
+                    c.L + at(k + 2, k + 1), c.ld, c.sb, rows2, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, ps)) != cudaSuccess)
+        return e;
+      // (c) rest of the trailing update of step k (independent of the panel): lower tiles of A[k+2:, k+2:]
+      if ((e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 2, k), c.ld, c.sb, c.A + at(k + 2, k + 2), c.ld,
+                    c.sb, rows2, rows2, NB, -1.0, 1.0, 1, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+    }
+    if (aux) {
+      if ((e = cudaEventRecord(aux->ev_aux, aux->st)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(c.st, aux->ev_aux, 0)) != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
+}
+
+// M21 = -M22 L21 M11 for the node [off, off+n) split at h (general, sequential; used when np/NB is not a power of 2)
+static cudaError_t trtri_rec(const FactorCtx& c, int off, int n, int NB) {
+  if (n <= NB) return cudaSuccess;
+  cudaError_t e;
+  const int h = ((n / NB) + 1) / 2 * NB, m = n - h;
+  if ((e = trtri_rec(c, off, h, NB)) != cudaSuccess) return e;
+  if ((e = trtri_rec(c, off + h, m, NB)) != cudaSuccess) return e;
+  const long long d0 = (long long)off * c.ld + off;
+  const long long o21 = (long long)(off + h) * c.ld + off, o22 = (long long)(off + h) * c.ld + off + h;
+  if ((e = gemm(true, false, c.M + o22, c.ld, c.sb, c.L + o21, c.ld, c.sb, c.A + o21, c.ld, c.sb, m, h, m, 1.0, 0.0, 0,
+                K_LE_ROW, c.batch, c.st)) != cudaSuccess) return e;
+  return gemm(true, false, c.A + o21, c.ld, c.sb, c.M + d0, c.ld, c.sb, c.M + o21, c.ld, c.sb, m, h, h, -1.0, 0.0, 0,
+              K_GE_COL, c.batch, c.st);
+}
+
+static cudaError_t trtri_bottom_up(const FactorCtx& c, int np) {
+  int NB = outer_nb();
+  if (np % NB != 0) NB = BASE_N;
+  const int nblk = np / NB;
+  if (nblk & (nblk - 1)) return trtri_rec(c, 0, np, NB);      // not a power of two: plain recursion
+  cudaError_t e;
+  for (int h = NB; h < np; h *= 2) {
+    const int nodes = np / (2 * h);
+    const long long node_stride = (long long)2 * h * (c.ld + 1);
+    const long long o21 = (long long)h * c.ld, o22 = (long long)h * c.ld + h;
+    // T = M22 L21 -> A21 (dead after the factorisation)
+    if ((e = gemm(true, false, c.M + o22, c.ld, c.sb, c.L + o21, c.ld, c.sb, c.A + o21, c.ld, c.sb, h, h, h, 1.0, 0.0, 0,
+                  K_LE_ROW, c.batch, c.st, nodes, node_stride, node_stride, node_stride)) != cudaSuccess) return e;
+    // M21 = -T M11
+    if ((e = gemm(true, false, c.A + o21, c.ld, c.sb, c.M, c.ld, c.sb, c.M + o21, c.ld, c.sb, h, h, h, -1.0, 0.0, 0,
+                  K_GE_COL, c.batch, c.st, nodes, node_stride, node_stride, node_stride)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 static bool g_attr_done = false;
 static cudaError_t ensure_attrs() {
   if (g_attr_done) return cudaSuccess;
@@ -229,7 +360,9 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   kernel_matrix_kernel<<<dim3(w.np / 64, w.np / 64, nb), 256, 0, st>>>(kp);
   FFGP_LAUNCHED();
   FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};
-  FFGP_CUDA(factor_rec(c, 0, w.np));
+  // look-ahead needs spare SMs: with a large batch every launch already fills the machine
+  FFGP_CUDA(potrf_right_looking(c, w.np, /*lookahead=*/nb < 8));
+  FFGP_CUDA(trtri_bottom_up(c, w.np));
   return 0;
 }
 
@@ -367,7 +500,7 @@ int ffgp_dense_nll_f64(const double* x, const double* y, const double* inv_ls, c
     grad_contract_kernel<<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
     FFGP_LAUNCHED();
     if (amp) {
-      grad_finish_kernel<<<nb, 128, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,
+      grad_finish_kernel<<<dim3(d + 1, nb), 256, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,
                                              g_inv_ls + (long long)b0 * d, g_amp + b0);
       FFGP_LAUNCHED();
     }

@@ -174,9 +174,10 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
 #pragma unroll
       for (int k = 0; k < c; k++) s = fma(-l[c][k], l[c][k], s);
       if (!(s > 0.0) && !failed) { failed = true; fail_col = j0 + c; }
-      const double dsq = sqrt(s);
-      l[c][c] = dsq;
-      inv[c] = 1.0 / dsq;
+      // one rsqrt replaces sqrt + division on the serial chain (l_cc = s * rsqrt(s), 1/l_cc = rsqrt(s))
+      const double rs = rsqrt(s);
+      inv[c] = rs;
+      l[c][c] = s * rs;
 #pragma unroll
       for (int r = c + 1; r < 8; r++) {
         double v = l[r][c];
@@ -306,7 +307,19 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
 #pragma unroll
   for (int c = 0; c < DMAX; c++) acc[c] = 0.0;
   const int kend = min(row + 1, n);
-  for (int k = lane; k < kend; k += 32) {
+  int k = lane;
+  for (; k + 96 < kend; k += 128) {            // 4 independent loads in flight per lane
+    const double m0 = m[k], m1 = m[k + 32], m2 = m[k + 64], m3 = m[k + 96];
+#pragma unroll
+    for (int c = 0; c < DMAX; c++)
+      if (c < D) {
+        acc[c] = fma(m0, y[(long long)k * D + c], acc[c]);
+        acc[c] = fma(m1, y[(long long)(k + 32) * D + c], acc[c]);
+        acc[c] = fma(m2, y[(long long)(k + 64) * D + c], acc[c]);
+        acc[c] = fma(m3, y[(long long)(k + 96) * D + c], acc[c]);
+      }
+  }
+  for (; k < kend; k += 32) {
     const double mv = m[k];
 #pragma unroll
     for (int c = 0; c < DMAX; c++)
@@ -360,7 +373,23 @@ __global__ void __launch_bounds__(256) colsum_weighted_kernel(const double* __re
 #pragma unroll
   for (int q = 0; q < QMAX; q++) acc[q] = 0.0;
   const int p_lo = lower ? c0 : 0;
-  for (int pp = p_lo + warp; pp < P; pp += 8) {
+  int pp = p_lo + warp;
+  for (; pp + 24 < P; pp += 32) {               // 4 independent row loads in flight per warp
+    double mv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) mv[u] = mat[(long long)(pp + 8 * u) * ld + c0 + lane];
+    if (square) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) acc[0] = fma(mv[u], mv[u], acc[0]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int q = 0; q < QMAX; q++)
+          if (q < Q) acc[q] = fma(mv[u], w[(long long)(pp + 8 * u) * ldw + q], acc[q]);
+    }
+  }
+  for (; pp < P; pp += 8) {
     const double mv = mat[(long long)pp * ld + c0 + lane];
     if (square) {
       acc[0] = fma(mv, mv, acc[0]);
@@ -551,18 +580,26 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
   }
 }
 
-// g_w[k] = -(1/w_k) sum_t partial[t][k];  g_amp = sum_t partial[t][d]  (partials of G o K/amp)
-__global__ void __launch_bounds__(128) grad_finish_kernel(const double* __restrict__ partial, int npart, int d,
+// g_w[k] = -(1/w_k) sum_t partial[t][k];  g_amp = sum_t partial[t][d]  (partials of G o K/amp).
+// grid (d+1, batch): each CTA reduces one component over all tiles with a fixed-order tree.
+__global__ void __launch_bounds__(256) grad_finish_kernel(const double* __restrict__ partial, int npart, int d,
                                                           const double* __restrict__ w, long long sw,
                                                           const double* __restrict__ amp, long long samp,
                                                           double* __restrict__ g_w, double* __restrict__ g_amp) {
-  const int b = blockIdx.x;
-  for (int k = threadIdx.x; k <= d; k += blockDim.x) {
-    double s = 0.0;
-    const double* pp = partial + (long long)b * npart * (d + 1) + k;
-    for (int t = 0; t < npart; t++) s += pp[(long long)t * (d + 1)];
-    if (k < d) g_w[(long long)b * d + k] = -s / w[b * sw + k];
-    else g_amp[b] = s;
+  __shared__ double red[256];
+  const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const double* pp = partial + (long long)b * npart * (d + 1) + k;
+  double s = 0.0;
+  for (int t = tid; t < npart; t += 256) s += pp[(long long)t * (d + 1)];
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (k < d) g_w[(long long)b * d + k] = -red[0] / w[b * sw + k];
+    else g_amp[b] = red[0];
   }
 }
 

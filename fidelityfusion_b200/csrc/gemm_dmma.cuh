@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace ffgp {
 
@@ -36,6 +37,8 @@ struct GemmParams {
   int M, N, K;
   int lda, ldb, ldc;
   long long sA, sB, sC;   // batch strides in elements
+  int inner;              // blockIdx.z = outer * inner + j: a second (inner) batch level, e.g. the nodes of one
+  long long iA, iB, iC;   //   level of the bottom-up triangular inverse inside each problem of the outer batch
   double alpha, beta;     // C = alpha * A.B + beta * C
   int lower_only;         // 1: only tiles with tj <= ti (needs BM == BN, M == N)
   int kmode;
@@ -112,9 +115,10 @@ gemm_dmma_kernel(const GemmParams p) {
   else if (p.kmode == K_GE_ROW) k_lo = i0;
   const int KT = (k_hi - k_lo) / BK;
 
-  const double* __restrict__ Ag = p.A + (long long)blockIdx.z * p.sA;
-  const double* __restrict__ Bg = p.B + (long long)blockIdx.z * p.sB;
-  double* __restrict__ Cg = p.C + (long long)blockIdx.z * p.sC;
+  const int zo = blockIdx.z / p.inner, zi = blockIdx.z - zo * p.inner;
+  const double* __restrict__ Ag = p.A + (long long)zo * p.sA + (long long)zi * p.iA;
+  const double* __restrict__ Bg = p.B + (long long)zo * p.sB + (long long)zi * p.iB;
+  double* __restrict__ Cg = p.C + (long long)zo * p.sC + (long long)zi * p.iC;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -219,41 +223,45 @@ gemm_dmma_kernel(const GemmParams p) {
   }
 }
 
-// Host launcher.  big = 128x128x16 tiles on 8 warps (one CTA per SM, 2 warps per
-// sub-partition); small = 64x64x16 tiles on 4 warps for the levels of the recursion where
-// 128-tiles would leave most of the 148 SMs idle.
+// Host launcher.  big = 128x128 tiles (one CTA per SM); small = 64x64x16 tiles on 4 warps for the levels where
+// 128-tiles would leave most of the 148 SMs idle.  The big-tile variant (warp grid, BK, stages) is selectable
+// with FFGP_GEMM_CFG for tuning; the default is the one measured fastest (see profiles/).
+template <int BM, int BN, int BK, int WM_, int WN_, int ST, bool A_KMAJ, bool B_KMAJ>
+cudaError_t launch_cfg(const GemmParams& p, int batch, cudaStream_t st) {
+  using Cfg = GemmCfg<BM, BN, BK, WM_, WN_, ST, A_KMAJ, B_KMAJ>;
+  auto kern = gemm_dmma_kernel<BM, BN, BK, WM_, WN_, ST, A_KMAJ, B_KMAJ>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tm = p.M / BM, tn = p.N / BN;
+  const int tiles = p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  if (tiles == 0 || batch == 0) return cudaSuccess;
+  kern<<<dim3(tiles, 1, batch), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
+inline int gemm_big_cfg() {
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("FFGP_GEMM_CFG");
+    cfg = e ? atoi(e) : 0;
+    if (cfg < 0 || cfg > 3) cfg = 0;
+  }
+  return cfg;
+}
+
 template <bool A_KMAJ, bool B_KMAJ>
 cudaError_t launch_gemm(const GemmParams& p, int batch, bool big, cudaStream_t st) {
-  if (big) {
-    constexpr int BM = 128, BN = 128, BK = 16, ST = 3;
-    using Cfg = GemmCfg<BM, BN, BK, 2, 4, ST, A_KMAJ, B_KMAJ>;
-    auto kern = gemm_dmma_kernel<BM, BN, BK, 2, 4, ST, A_KMAJ, B_KMAJ>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    const int tm = p.M / BM, tn = p.N / BN;
-    const int tiles = p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
-    if (tiles == 0 || batch == 0) return cudaSuccess;
-    kern<<<dim3(tiles, 1, batch), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
-  } else {
-    constexpr int BM = 64, BN = 64, BK = 16, ST = 3;
-    using Cfg = GemmCfg<BM, BN, BK, 2, 2, ST, A_KMAJ, B_KMAJ>;
-    auto kern = gemm_dmma_kernel<BM, BN, BK, 2, 2, ST, A_KMAJ, B_KMAJ>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    const int tm = p.M / BM, tn = p.N / BN;
-    const int tiles = p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
-    if (tiles == 0 || batch == 0) return cudaSuccess;
-    kern<<<dim3(tiles, 1, batch), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  if (!big) return launch_cfg<64, 64, 16, 2, 2, 3, A_KMAJ, B_KMAJ>(p, batch, st);
+  switch (gemm_big_cfg()) {
+    case 1: return launch_cfg<128, 128, 16, 4, 4, 3, A_KMAJ, B_KMAJ>(p, batch, st);   // 16 warps, 32x32 warp tiles
+    case 2: return launch_cfg<128, 128, 32, 2, 4, 2, A_KMAJ, B_KMAJ>(p, batch, st);   // BK 32, double buffer
+    case 3: return launch_cfg<128, 128, 32, 4, 4, 2, A_KMAJ, B_KMAJ>(p, batch, st);
+    default: return launch_cfg<128, 128, 16, 2, 4, 3, A_KMAJ, B_KMAJ>(p, batch, st);  // 8 warps, 64x32 warp tiles
   }
-  return cudaGetLastError();
 }
 
 }  // namespace ffgp
