@@ -26,27 +26,50 @@ EPS = 1e-9
 def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True):
     """x [B,n,d], y [B,n,D], length_scales [B,d], signal_variance [B], log_beta [B] (raw reference parameters),
     xs [B,ns,d] or None.  Returns dict: nll [B] (= -cigp.negative_log_likelihood), g_length_scales [B,d],
-    g_signal_variance [B], g_log_beta [B], and mean [B,ns,D], var [B,ns] (diag of cigp.forward's covariance)."""
+    g_signal_variance [B], g_log_beta [B], and mean [B,ns,D], var [B,ns] (diag of cigp.forward's covariance).
+
+    ONE C call (ffgp_dense_fit_f64): every problem is factorised once and the NLL, its analytic gradient and the
+    posterior all come from that factor; the chain rule to the reference's raw parameters is a few vector ops."""
+    from . import _lib as B
+    L = B.lib()
     Bn, n, d = x.shape
     D = y.shape[2]
-    ls = length_scales.detach().clone().requires_grad_(want_grad)
-    sv = signal_variance.detach().clone().requires_grad_(want_grad)
-    lb = log_beta.detach().clone().requires_grad_(want_grad)
-    inv_ls = 1.0 / (ls.abs() + EPS)
-    amp = sv.abs()
+    dev = x.device
+    f64 = lambda t: t.detach().to(torch.float64).contiguous()
+    xc, yc = f64(x), f64(y)
+    ls, sv, lb = f64(length_scales), f64(signal_variance).reshape(Bn), f64(log_beta).reshape(Bn)
+    ell = ls.abs() + EPS
+    inv_ls = (1.0 / ell).contiguous()
+    amp = sv.abs().contiguous()
     noise = torch.exp(-lb)
-    diag = (noise + JITTER).unsqueeze(1).expand(Bn, n)
-    core = ops.dense_nll(x, y, inv_ls, amp, diag_add=diag, clamp=True)
-    nll = core + 0.5 * n * D * math.log(2 * PI)
-    out = {'nll': nll.detach()}
+    diag = (noise + JITTER).unsqueeze(1).expand(Bn, n).contiguous()
+    ns = 0 if xs is None else xs.shape[1]
+    xsc = f64(xs) if xs is not None else None
+    nll = torch.empty(Bn, dtype=torch.float64, device=dev)
+    alpha = torch.empty(Bn, n, D, dtype=torch.float64, device=dev)
+    g_il = torch.empty(Bn, d, dtype=torch.float64, device=dev) if want_grad else None
+    g_amp = torch.empty(Bn, dtype=torch.float64, device=dev) if want_grad else None
+    g_diag = torch.empty(Bn, n, dtype=torch.float64, device=dev) if want_grad else None
+    mean = torch.empty(Bn, ns, D, dtype=torch.float64, device=dev) if ns else None
+    var = torch.empty(Bn, ns, dtype=torch.float64, device=dev) if ns else None
+    info = torch.empty(Bn, dtype=torch.int32, device=dev)
+    wsb = L.ffgp_dense_workspace_bytes(n, d, D, ns, Bn)
+    ws = ops._ws_cache.get(wsb, dev)
+    noise_c = noise.contiguous()
+    rc = L.ffgp_dense_fit_f64(B.ptr(xc), B.ptr(yc), B.ptr(xsc), B.ptr(inv_ls), B.ptr(amp), B.ptr(diag), None, None, None,
+                              B.ptr(noise_c), n, d, D, ns, Bn, 1, 1, 1, int(want_grad), 0, 0, B.ptr(ws), wsb,
+                              B.ptr(nll), None, B.ptr(alpha), B.ptr(g_il), B.ptr(g_amp), B.ptr(g_diag), None,
+                              B.ptr(mean), B.ptr(var), B.ptr(info), B.stream_ptr())
+    B.check(rc, 'ffgp_dense_fit_f64')
+    ops.check_info(info)
+    out = {'nll': nll + 0.5 * n * D * math.log(2 * PI)}
     if want_grad:
-        nll.sum().backward()
-        out.update(g_length_scales=ls.grad, g_signal_variance=sv.grad, g_log_beta=lb.grad)
-    if xs is not None:
-        with torch.no_grad():
-            mean, var = ops.dense_predict(x, y, xs, inv_ls.detach(), amp.detach(), diag_add=diag.detach(),
-                                          cov_offset=noise.detach(), full_cov=False, clamp=True)
-        out.update(mean=mean, var=var)
+        out['g_length_scales'] = g_il * (-1.0 / (ell * ell)) * torch.sign(ls)       # inv_ls = 1/(|ls|+eps)
+        out['g_signal_variance'] = g_amp * torch.sign(sv)                           # amp = |sv|
+        out['g_log_beta'] = g_diag.sum(1) * (-noise)                                # diag = e^-lb + jitter
+    if ns:
+        out['mean'] = mean
+        out['var'] = var
     return out
 
 

@@ -448,85 +448,36 @@ int ffgp_kernel_matrix_f64(const double* x1, const double* x2, const double* inv
   return 0;
 }
 
-int ffgp_dense_nll_f64(const double* x, const double* y, const double* inv_ls, const double* amp, const double* diag_add,
-                       const double* sigma_add, int n, int d, int D, int batch, int params_batched, int clamp,
-                       int want_grad, void* workspace, size_t workspace_bytes, double* out_nll, double* out_logdet,
-                       double* out_alpha, double* g_inv_ls, double* g_amp, double* g_diag, double* g_sigma, int* info,
-                       void* stream) {
-  if (!y || !workspace || !out_nll || !info) return fail(-1, "ffgp_dense_nll_f64: null pointer");
-  if (amp && (!x || !inv_ls)) return fail(-1, "ffgp_dense_nll_f64: kernel term needs x and inv_ls");
-  if (!amp && !sigma_add) return fail(-1, "ffgp_dense_nll_f64: neither a kernel nor a covariance was given");
-  if (n <= 0 || D <= 0 || batch <= 0 || d < 0) return fail(-2, "ffgp_dense_nll_f64: bad size");
-  if (amp && d > GRAD_DMAX && want_grad) return fail(-2, "ffgp_dense_nll_f64: d > 64 not supported with want_grad");
-  if (want_grad && amp && (!g_inv_ls || !g_amp)) return fail(-1, "ffgp_dense_nll_f64: gradient outputs missing");
+int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const double* inv_ls, const double* amp,
+                       const double* diag_add, const double* sigma_add, const double* Ks, const double* Kss,
+                       const double* cov_offset, int n, int d, int D, int ns, int batch, int params_batched, int clamp,
+                       int want_nll, int want_grad, int full_cov, int reuse_factor, void* workspace, size_t workspace_bytes,
+                       double* out_nll, double* out_logdet, double* out_alpha, double* g_inv_ls, double* g_amp,
+                       double* g_diag, double* g_sigma, double* out_mean, double* out_cov, int* info, void* stream) {
+  const bool want_pred = out_mean != nullptr;
+  if (!y || !workspace || !info) return fail(-1, "ffgp_dense_fit_f64: null pointer");
+  if (want_nll && !out_nll) return fail(-1, "ffgp_dense_fit_f64: out_nll missing");
+  if (amp && (!x || !inv_ls)) return fail(-1, "ffgp_dense_fit_f64: kernel term needs x and inv_ls");
+  if (!amp && !sigma_add) return fail(-1, "ffgp_dense_fit_f64: neither a kernel nor a covariance was given");
+  if (n <= 0 || D <= 0 || batch <= 0 || d < 0 || ns < 0) return fail(-2, "ffgp_dense_fit_f64: bad size");
+  if (amp && d > GRAD_DMAX && want_grad) return fail(-2, "ffgp_dense_fit_f64: d > 64 not supported with want_grad");
+  if (want_grad && amp && (!g_inv_ls || !g_amp)) return fail(-1, "ffgp_dense_fit_f64: gradient outputs missing");
+  if (want_pred) {
+    if (ns <= 0) return fail(-2, "ffgp_dense_fit_f64: ns must be positive when predictions are requested");
+    if (amp && !xs) return fail(-1, "ffgp_dense_fit_f64: kernel term needs xs for predictions");
+    if (!amp && !Ks) return fail(-1, "ffgp_dense_fit_f64: covariance mode needs Ks");
+    if (!amp && out_cov && !Kss) return fail(-1, "ffgp_dense_fit_f64: covariance mode needs Kss for out_cov");
+    if (!amp && out_cov && !full_cov) return fail(-2, "ffgp_dense_fit_f64: covariance mode returns the full covariance");
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  DenseWs w = layout_ws(n, d, D, 0, batch, (char*)workspace);
-  if (workspace_bytes < w.bytes) return fail(-3, "ffgp_dense_nll_f64: workspace too small");
+  DenseWs w = layout_ws(n, d, D, want_pred ? ns : 0, batch, (char*)workspace);
+  if (workspace_bytes < w.bytes) return fail(-3, "ffgp_dense_fit_f64: workspace too small");
+  if (reuse_factor && batch > w.chunk) return fail(-4, "ffgp_dense_fit_f64: reuse_factor needs batch <= one chunk");
+  if (reuse_factor && (want_nll || want_grad)) return fail(-4, "ffgp_dense_fit_f64: reuse_factor is for prediction only");
   FFGP_CUDA(ensure_attrs());
   DenseArgs a{x, y, inv_ls, amp, diag_add, sigma_add, n, d, D, batch, params_batched, /*diag_batched=*/params_batched, clamp};
-  FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
-  const long long sM = (long long)w.np * w.np;
-  for (int b0 = 0; b0 < batch; b0 += w.chunk) {
-    const int nb = std::min(w.chunk, batch - b0);
-    int rc;
-    if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
-    if ((rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
-    nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, D, out_nll + b0,
-                                          out_logdet ? out_logdet + b0 : nullptr);
-    FFGP_LAUNCHED();
-    if ((rc = copy_alpha_out(a, w, b0, nb, out_alpha, st)) != 0) return rc;
-    if (!want_grad) continue;
-    // S = M^T M (lower) into the dead A buffer
-    FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
-    int src_is_G = 0;
-    if (w.gemm_rhs) {   // G = 0.5 (D S - alpha alpha^T) through the GEMM epilogue
-      const long long sG = (long long)w.np * w.Dp;
-      FFGP_CUDA(gemm(true, true, w.alpha, w.Dp, sG, w.alpha, w.Dp, sG, w.A, w.np, sM, w.np, w.np, w.Dp, -0.5, 0.5 * D, 1,
-                     K_FULL, nb, st));
-      src_is_G = 1;
-    }
-    GradParams gp;
-    memset(&gp, 0, sizeof(gp));
-    gp.src = w.A; gp.ld = w.np; gp.ssrc = sM;
-    gp.x = x ? x + (long long)b0 * n * d : nullptr; gp.n = n; gp.d = amp ? d : 0; gp.sx = (long long)n * d;
-    gp.w = inv_ls ? inv_ls + (params_batched ? (long long)b0 * d : 0) : nullptr; gp.sw = params_batched ? d : 0;
-    gp.amp = amp ? amp + (params_batched ? b0 : 0) : nullptr; gp.samp = params_batched ? 1 : 0;
-    gp.alpha = w.alpha; gp.D = D; gp.salpha = (long long)w.np * D;
-    gp.src_is_G = src_is_G;
-    gp.partial = w.partial; gp.npart = w.ngtile;
-    gp.g_diag = g_diag ? g_diag + (long long)b0 * n : nullptr; gp.sgd = n;
-    gp.G_out = g_sigma ? g_sigma + (long long)b0 * n * n : nullptr; gp.sGo = (long long)n * n;
-    gp.have_k = amp ? 1 : 0;
-    grad_contract_kernel<<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
-    FFGP_LAUNCHED();
-    if (amp) {
-      grad_finish_kernel<<<dim3(d + 1, nb), 256, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,
-                                             g_inv_ls + (long long)b0 * d, g_amp + b0);
-      FFGP_LAUNCHED();
-    }
-  }
-  return 0;
-}
-
-int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, const double* inv_ls, const double* amp,
-                           const double* diag_add, const double* sigma_add, const double* Ks, const double* Kss,
-                           const double* cov_offset, int n, int d, int D, int ns, int batch, int params_batched,
-                           int clamp, int full_cov, int reuse_factor, void* workspace, size_t workspace_bytes,
-                           double* out_mean, double* out_cov, int* info, void* stream) {
-  if (!y || !workspace || !out_mean || !info) return fail(-1, "ffgp_dense_predict_f64: null pointer");
-  if (amp && (!x || !xs || !inv_ls)) return fail(-1, "ffgp_dense_predict_f64: kernel term needs x, xs and inv_ls");
-  if (!amp && (!sigma_add || !Ks)) return fail(-1, "ffgp_dense_predict_f64: covariance mode needs sigma_add and Ks");
-  if (!amp && out_cov && !Kss) return fail(-1, "ffgp_dense_predict_f64: covariance mode needs Kss for out_cov");
-  if (!amp && out_cov && !full_cov) return fail(-2, "ffgp_dense_predict_f64: covariance mode returns the full covariance");
-  if (n <= 0 || D <= 0 || batch <= 0 || ns <= 0 || d < 0) return fail(-2, "ffgp_dense_predict_f64: bad size");
-  cudaStream_t st = (cudaStream_t)stream;
-  DenseWs w = layout_ws(n, d, D, ns, batch, (char*)workspace);
-  if (workspace_bytes < w.bytes) return fail(-3, "ffgp_dense_predict_f64: workspace too small");
-  if (reuse_factor && batch > w.chunk) return fail(-4, "ffgp_dense_predict_f64: reuse_factor needs batch <= one chunk");
-  FFGP_CUDA(ensure_attrs());
-  DenseArgs a{x, y, inv_ls, amp, diag_add, sigma_add, n, d, D, batch, params_batched, params_batched, clamp};
   if (!reuse_factor) FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
-  const long long sM = (long long)w.np * w.np, sKx = (long long)w.np * w.nsp, sKxx = (long long)w.nsp * w.nsp;
+  const long long sM = (long long)w.np * w.np;
   for (int b0 = 0; b0 < batch; b0 += w.chunk) {
     const int nb = std::min(w.chunk, batch - b0);
     int rc;
@@ -534,7 +485,45 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, c
       if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
       if ((rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
     }
-    // Kx = K(x, xs)  [np][nsp]   (or the caller's Ks, padded)
+    if (want_nll) {
+      nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, D, out_nll + b0,
+                                            out_logdet ? out_logdet + b0 : nullptr);
+      FFGP_LAUNCHED();
+    }
+    if (!reuse_factor && (rc = copy_alpha_out(a, w, b0, nb, out_alpha, st)) != 0) return rc;
+    if (want_grad) {
+      // S = M^T M (lower) into the dead A buffer
+      FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
+      int src_is_G = 0;
+      if (w.gemm_rhs) {   // G = 0.5 (D S - alpha alpha^T) through the GEMM epilogue
+        const long long sG = (long long)w.np * w.Dp;
+        FFGP_CUDA(gemm(true, true, w.alpha, w.Dp, sG, w.alpha, w.Dp, sG, w.A, w.np, sM, w.np, w.np, w.Dp, -0.5, 0.5 * D, 1,
+                       K_FULL, nb, st));
+        src_is_G = 1;
+      }
+      GradParams gp;
+      memset(&gp, 0, sizeof(gp));
+      gp.src = w.A; gp.ld = w.np; gp.ssrc = sM;
+      gp.x = x ? x + (long long)b0 * n * d : nullptr; gp.n = n; gp.d = amp ? d : 0; gp.sx = (long long)n * d;
+      gp.w = inv_ls ? inv_ls + (params_batched ? (long long)b0 * d : 0) : nullptr; gp.sw = params_batched ? d : 0;
+      gp.amp = amp ? amp + (params_batched ? b0 : 0) : nullptr; gp.samp = params_batched ? 1 : 0;
+      gp.alpha = w.alpha; gp.D = D; gp.salpha = (long long)w.np * D;
+      gp.src_is_G = src_is_G;
+      gp.partial = w.partial; gp.npart = w.ngtile;
+      gp.g_diag = g_diag ? g_diag + (long long)b0 * n : nullptr; gp.sgd = n;
+      gp.G_out = g_sigma ? g_sigma + (long long)b0 * n * n : nullptr; gp.sGo = (long long)n * n;
+      gp.have_k = amp ? 1 : 0;
+      grad_contract_kernel<<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
+      FFGP_LAUNCHED();
+      if (amp) {
+        grad_finish_kernel<<<dim3(d + 1, nb), 256, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,
+                                                            g_inv_ls + (long long)b0 * d, g_amp + b0);
+        FFGP_LAUNCHED();
+      }
+    }
+    if (!want_pred) continue;
+    // ---------------- posterior at xs, from the factor that is still resident (M, alpha) ----------------
+    const long long sKx = (long long)w.np * w.nsp, sKxx = (long long)w.nsp * w.nsp;
     KernelMatrixParams kp;
     memset(&kp, 0, sizeof(kp));
     kp.n1 = n; kp.n2 = ns; kp.d = d; kp.np1 = w.np; kp.np2 = w.nsp; kp.ldk = w.nsp; kp.sK = sKx; kp.K = w.Kx;
@@ -602,6 +591,27 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, c
     }
   }
   return 0;
+}
+
+int ffgp_dense_nll_f64(const double* x, const double* y, const double* inv_ls, const double* amp, const double* diag_add,
+                       const double* sigma_add, int n, int d, int D, int batch, int params_batched, int clamp,
+                       int want_grad, void* workspace, size_t workspace_bytes, double* out_nll, double* out_logdet,
+                       double* out_alpha, double* g_inv_ls, double* g_amp, double* g_diag, double* g_sigma, int* info,
+                       void* stream) {
+  return ffgp_dense_fit_f64(x, y, nullptr, inv_ls, amp, diag_add, sigma_add, nullptr, nullptr, nullptr, n, d, D, 0, batch,
+                            params_batched, clamp, 1, want_grad, 0, 0, workspace, workspace_bytes, out_nll, out_logdet,
+                            out_alpha, g_inv_ls, g_amp, g_diag, g_sigma, nullptr, nullptr, info, stream);
+}
+
+int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs, const double* inv_ls, const double* amp,
+                           const double* diag_add, const double* sigma_add, const double* Ks, const double* Kss,
+                           const double* cov_offset, int n, int d, int D, int ns, int batch, int params_batched,
+                           int clamp, int full_cov, int reuse_factor, void* workspace, size_t workspace_bytes,
+                           double* out_mean, double* out_cov, int* info, void* stream) {
+  if (!out_mean) return fail(-1, "ffgp_dense_predict_f64: null pointer");
+  return ffgp_dense_fit_f64(x, y, xs, inv_ls, amp, diag_add, sigma_add, Ks, Kss, cov_offset, n, d, D, ns, batch,
+                            params_batched, clamp, 0, 0, full_cov, reuse_factor, workspace, workspace_bytes, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_mean, out_cov, info, stream);
 }
 
 int ffgp_potrf_trtri_f64(const double* A, int n, int batch, void* workspace, size_t workspace_bytes, double* L,

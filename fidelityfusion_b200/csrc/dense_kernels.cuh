@@ -137,63 +137,89 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixPa
 // The forward substitution L M = I is carried along with the factorisation (the rank-8 update
 // of panel p is applied to the rows below it in BOTH the trailing part of A and the running
 // inverse), so potrf and trtri share every pass over shared memory.
-// smem T[128][130]: T[i][k], k<=i holds A/L; T[c][i+1], c<=i holds R[i][c] (running inverse).
+// smem T[128][129]: T[i][k], k<=i holds A/L; T[c][i+1], c<=i holds R[i][c] (running inverse).
+// The odd row stride makes both row-wise and column-wise warp accesses bank-conflict free.
+// Per 8-column panel:  (a) the 8x8 diagonal factor is NOT on the critical path: warp 0 updates the next
+// diagonal block first and factors it (every lane redundantly, in registers) while the other warps finish the
+// rank-8 update (look-ahead inside the CTA);  (b) one thread per row solves the panel / one per column scales
+// the inverse's row block;  (c) rank-8 update with a warp per 4-row group: the row operand is a broadcast, the
+// column operand (8 x 128, shared by every row group) is hoisted into registers once per panel.
 // ------------------------------------------------------------------------------------------
 constexpr int BASE_N = 128;
-constexpr int BASE_LD = 130;
-constexpr size_t BASE_SMEM = (size_t)BASE_N * BASE_LD * sizeof(double) + 64 * sizeof(double);
+constexpr int BASE_LD = 129;
+constexpr size_t BASE_SMEM = ((size_t)BASE_N * BASE_LD + 48 + 64) * sizeof(double);
+
+// Cholesky of an 8x8 block held in registers (lower part of l), returns first failing column or -1.
+__device__ __forceinline__ int chol8_regs(double (&l)[8][8], double (&inv)[8]) {
+  int fail = -1;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    double s = l[c][c];
+#pragma unroll
+    for (int k = 0; k < c; k++) s = fma(-l[c][k], l[c][k], s);
+    if (!(s > 0.0) && fail < 0) fail = c;
+    // one rsqrt replaces sqrt + division on the serial chain (l_cc = s * rsqrt(s), 1/l_cc = rsqrt(s))
+    const double rs = rsqrt(s);
+    inv[c] = rs;
+    l[c][c] = s * rs;
+#pragma unroll
+    for (int r = c + 1; r < 8; r++) {
+      double v = l[r][c];
+#pragma unroll
+      for (int k = 0; k < c; k++) v = fma(-l[r][k], l[c][k], v);
+      l[r][c] = v * rs;
+    }
+  }
+  return fail;
+}
 
 __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
     const double* __restrict__ A, double* __restrict__ L, double* __restrict__ M, int ld, long long sbatch,
     double* __restrict__ logdet_part, int logdet_stride, int blk, int* __restrict__ info, int row_offset) {
   extern __shared__ __align__(16) double sm[];
-  double (*T)[BASE_LD] = reinterpret_cast<double (*)[BASE_LD]>(sm);
-  double* red = sm + BASE_N * BASE_LD;
-  const int tid = threadIdx.x, b = blockIdx.x;
+  double* T = sm;                                   // [128][129]
+  double* Fnext = sm + BASE_N * BASE_LD;            // 36 factor entries + 8 inverses + fail column
+  double* red = Fnext + 48;
+  const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
   A += b * sbatch; L += b * sbatch; M += b * sbatch;
+#define TT(i, k) T[(i) * BASE_LD + (k)]
   for (int e = tid; e < BASE_N * BASE_N; e += 256) {
     const int i = e >> 7, k = e & 127;
     if (k <= i) {
-      T[i][k] = A[(long long)i * ld + k];
-      T[k][i + 1] = (i == k) ? 1.0 : 0.0;
+      TT(i, k) = A[(long long)i * ld + k];
+      TT(k, i + 1) = (i == k) ? 1.0 : 0.0;
     }
   }
-  bool failed = false;
-  int fail_col = 0;
+  int fail_col = -1;
   for (int j0 = 0; j0 < BASE_N; j0 += 8) {
     __syncthreads();
-    // (a) every thread factors the 8x8 diagonal block redundantly in registers
     double l[8][8], inv[8];
+    if (j0 == 0) {
 #pragma unroll
-    for (int r = 0; r < 8; r++)
+      for (int r = 0; r < 8; r++)
 #pragma unroll
-      for (int c = 0; c <= r; c++) l[r][c] = T[j0 + r][j0 + c];
+        for (int c = 0; c <= r; c++) l[r][c] = TT(r, c);
+      const int f = chol8_regs(l, inv);
+      if (f >= 0 && fail_col < 0) fail_col = f;
+      __syncthreads();                               // everyone has read the block before (b) overwrites it
+    } else {
+      int q = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-      double s = l[c][c];
+      for (int r = 0; r < 8; r++)
 #pragma unroll
-      for (int k = 0; k < c; k++) s = fma(-l[c][k], l[c][k], s);
-      if (!(s > 0.0) && !failed) { failed = true; fail_col = j0 + c; }
-      // one rsqrt replaces sqrt + division on the serial chain (l_cc = s * rsqrt(s), 1/l_cc = rsqrt(s))
-      const double rs = rsqrt(s);
-      inv[c] = rs;
-      l[c][c] = s * rs;
+        for (int c = 0; c <= r; c++) l[r][c] = Fnext[q++];
 #pragma unroll
-      for (int r = c + 1; r < 8; r++) {
-        double v = l[r][c];
-#pragma unroll
-        for (int k = 0; k < c; k++) v = fma(-l[r][k], l[c][k], v);
-        l[r][c] = v * inv[c];
-      }
+      for (int c = 0; c < 8; c++) inv[c] = Fnext[36 + c];
+      const int f = (int)Fnext[44];
+      if (f >= 0 && fail_col < 0) fail_col = j0 + f;
     }
-    __syncthreads();     // everyone has read the diagonal block before it is overwritten
     // (b) panel rows: a <- a L11^-T ; inverse row block: v <- L11^-1 v
     if (tid < 128) {
       const int r = tid;
       if (r >= j0) {
         double a[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) a[c] = (j0 + c <= r) ? T[r][j0 + c] : 0.0;
+        for (int c = 0; c < 8; c++) a[c] = (j0 + c <= r) ? TT(r, j0 + c) : 0.0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
           double v = a[c];
@@ -203,14 +229,14 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
         }
 #pragma unroll
         for (int c = 0; c < 8; c++)
-          if (j0 + c <= r) T[r][j0 + c] = a[c];
+          if (j0 + c <= r) TT(r, j0 + c) = a[c];
       }
     } else {
       const int c = tid - 128;
       if (c < j0 + 8) {
         double v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (c <= j0 + k) ? T[c][j0 + k + 1] : 0.0;
+        for (int k = 0; k < 8; k++) v[k] = (c <= j0 + k) ? TT(c, j0 + k + 1) : 0.0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           double u = v[k];
@@ -220,23 +246,28 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
         }
 #pragma unroll
         for (int k = 0; k < 8; k++)
-          if (c <= j0 + k) T[c][j0 + k + 1] = v[k];
+          if (c <= j0 + k) TT(c, j0 + k + 1) = v[k];
       }
     }
     __syncthreads();
-    // (c) rank-8 update of every row below the panel, across the running inverse (virtual
-    //     columns < j0+8) and the trailing part of A (virtual columns j0+8 .. i); 4x4 micro-tiles
-    const int r_lo = (j0 + 8) >> 2;
-    const int ntile = (32 * 33) / 2 - (r_lo * (r_lo + 1)) / 2;
-    const int base_t = (r_lo * (r_lo + 1)) / 2;
-    for (int t = tid; t < ntile; t += 256) {
-      const int tt = t + base_t;
-      int ri = (int)((sqrtf(8.0f * (float)tt + 1.0f) - 1.0f) * 0.5f);
-      while (ri * (ri + 1) / 2 > tt) --ri;
-      while ((ri + 1) * (ri + 2) / 2 <= tt) ++ri;
-      const int ci = tt - ri * (ri + 1) / 2;
-      const int i = ri * 4, v0 = ci * 4;
-      const bool rpart = (v0 < j0 + 8);
+    // (c) rank-8 update of the rows below the panel.  Lane owns virtual columns v = lane + 32 q.
+    const int r0 = j0 + 8;
+    const int nquad = (BASE_N - r0) >> 2;
+    if (nquad == 0) continue;
+    double bv[8][4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int v = lane + 32 * q;
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) {
+        double x;
+        if (v < r0) x = (v <= j0 + kk) ? TT(v, j0 + kk + 1) : 0.0;     // running inverse, row block of the panel
+        else x = TT(v, j0 + kk);                                          // panel rows of L
+        bv[kk][q] = x;
+      }
+    }
+    auto do_quad = [&](int rq) {
+      const int i0 = r0 + 4 * rq;
       double cacc[4][4];
 #pragma unroll
       for (int a = 0; a < 4; a++)
@@ -244,48 +275,69 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
         for (int q = 0; q < 4; q++) cacc[a][q] = 0.0;
 #pragma unroll
       for (int kk = 0; kk < 8; kk++) {
-        double av[4], bv[4];
+        double av[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++) av[a] = T[i + a][j0 + kk];
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-          bv[q] = rpart ? ((v0 + q <= j0 + kk) ? T[v0 + q][j0 + kk + 1] : 0.0) : T[v0 + q][j0 + kk];
+        for (int a = 0; a < 4; a++) av[a] = TT(i0 + a, j0 + kk);
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int q = 0; q < 4; q++) cacc[a][q] = fma(av[a], bv[q], cacc[a][q]);
+          for (int q = 0; q < 4; q++) cacc[a][q] = fma(av[a], bv[kk][q], cacc[a][q]);
       }
-      if (rpart) {
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+      for (int q = 0; q < 4; q++) {
+        const int v = lane + 32 * q;
+        if (v < r0) {
 #pragma unroll
-          for (int q = 0; q < 4; q++) T[v0 + q][i + a + 1] -= cacc[a][q];
-      } else {
+          for (int a = 0; a < 4; a++) TT(v, i0 + a + 1) -= cacc[a][q];
+        } else {
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int q = 0; q < 4; q++)
-            if (v0 + q <= i + a) T[i + a][v0 + q] -= cacc[a][q];
+          for (int a = 0; a < 4; a++)
+            if (v <= i0 + a) TT(i0 + a, v) -= cacc[a][q];
+        }
       }
+    };
+    if (warp == 0) {
+      // look-ahead: the next diagonal block (row quads 0,1) first, then its factor for the next panel
+      do_quad(0);
+      if (nquad > 1) do_quad(1);
+      __syncwarp();
+      double ln[8][8], invn[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) ln[r][c] = TT(r0 + r, r0 + c);
+      const int f = chol8_regs(ln, invn);
+      if (lane == 0) {
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int c = 0; c <= r; c++) Fnext[q++] = ln[r][c];
+#pragma unroll
+        for (int c = 0; c < 8; c++) Fnext[36 + c] = invn[c];
+        Fnext[44] = (double)f;
+      }
+      for (int rq = 2 + 7; rq < nquad; rq += 8) do_quad(rq);
+    } else {
+      for (int rq = 2 + (warp - 1); rq < nquad; rq += 8) do_quad(rq);
     }
   }
   __syncthreads();
   for (int e = tid; e < BASE_N * BASE_N; e += 256) {
     const int i = e >> 7, k = e & 127;
-    L[(long long)i * ld + k] = (k <= i) ? T[i][k] : 0.0;
-    M[(long long)i * ld + k] = (k <= i) ? T[k][i + 1] : 0.0;
+    L[(long long)i * ld + k] = (k <= i) ? TT(i, k) : 0.0;
+    M[(long long)i * ld + k] = (k <= i) ? TT(k, i + 1) : 0.0;
   }
   // sum of log L_ii of this block, fixed order
-  if (tid < 128) red[tid & 63] = 0.0;
-  __syncthreads();
-  if (tid < 64) red[tid] = log(T[tid][tid]) + log(T[tid + 64][tid + 64]);
+  if (tid < 64) red[tid] = log(TT(tid, tid)) + log(TT(tid + 64, tid + 64));
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;
     for (int k = 0; k < 64; k++) s += red[k];
     logdet_part[(long long)b * logdet_stride + blk] = s;
-    if (failed) atomicCAS(info + b, 0, row_offset + fail_col + 1);
+    if (fail_col >= 0) atomicCAS(info + b, 0, row_offset + fail_col + 1);
   }
+#undef TT
 }
 
 // ------------------------------------------------------------------------------------------
@@ -499,6 +551,25 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
   const double* src = p.src + b * p.ssrc;
   double Wv[4][4];
   double sumW = 0.0;
+  // pass 1: squared distances of the 4x4 pairs, operands loaded once per input dimension
+  double sq[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) sq[a][q] = 0.0;
+  if (p.have_k) {
+    for (int k = 0; k < d; k++) {
+      double xr[4], xc[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) xr[a] = xi[(tr + 16 * a) * ldx + k];
+#pragma unroll
+      for (int q = 0; q < 4; q++) xc[q] = xj[(tc + 16 * q) * ldx + k];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const double dz = xr[a] - xc[q]; sq[a][q] = fma(dz, dz, sq[a][q]); }
+    }
+  }
 #pragma unroll
   for (int a = 0; a < 4; a++) {
     const int r = tr + 16 * a, gi = i0 + r;
@@ -523,9 +594,7 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
           if (p.g_diag) p.g_diag[b * p.sgd + gi] = G;
           wgt = G;                             // K_ii / amp = 1, dz = 0
         } else if (p.have_k) {
-          double sq = 0.0;
-          for (int k = 0; k < d; k++) { const double dz = xi[r * ldx + k] - xj[c * ldx + k]; sq = fma(dz, dz, sq); }
-          wgt = 2.0 * G * exp(-0.5 * sq);      // (i,j) and (j,i); amplitude applied below
+          wgt = 2.0 * G * exp(-0.5 * sq[a][q]);   // (i,j) and (j,i); amplitude applied below
         }
       }
       sumW += wgt;                             // sum G o (K / amp): d/d amp needs no division (amp may be 0)
@@ -535,33 +604,21 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
   const int warp = tid >> 5, lane = tid & 31;
   double* part = p.partial + ((long long)b * p.npart + t) * (d + 1);
   if (p.have_k) {
-    for (int k0 = 0; k0 < d; k0 += 16) {
-      double acc[16];
+    // pass 2: sum_pairs W dz_k^2 per input dimension, operands again loaded once per dimension
+    for (int k = 0; k < d; k++) {
+      double xr[4], xc[4];
 #pragma unroll
-      for (int k = 0; k < 16; k++) acc[k] = 0.0;
+      for (int a = 0; a < 4; a++) xr[a] = xi[(tr + 16 * a) * ldx + k];
 #pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int r = tr + 16 * a;
+      for (int q = 0; q < 4; q++) xc[q] = xj[(tc + 16 * q) * ldx + k];
+      double v = 0.0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int c = tc + 16 * q;
-          const double wgt = Wv[a][q];
+      for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int k = 0; k < 16; k++) {
-            if (k0 + k < d) {
-              const double dz = xi[r * ldx + k0 + k] - xj[c * ldx + k0 + k];
-              acc[k] = fma(wgt * dz, dz, acc[k]);
-            }
-          }
-        }
-      }
+        for (int q = 0; q < 4; q++) { const double dz = xr[a] - xc[q]; v = fma(Wv[a][q] * dz, dz, v); }
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && k0 + k < d) red[warp * (GRAD_DMAX + 1) + k0 + k] = v;
-      }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp * (GRAD_DMAX + 1) + k] = v;
     }
   }
   {

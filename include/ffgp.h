@@ -116,6 +116,21 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs,
                            double* out_mean, double* out_cov, int* info, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Fused fit: NLL (+ gradient) AND the posterior at xs from ONE factorisation per problem - what a BO acquisition
+ * sweep needs per candidate (train step, then predict: v1/CFKG.py:124-129 re-trains and predicts per candidate).
+ * Same arguments as ffgp_dense_nll_f64 + ffgp_dense_predict_f64; out_mean == NULL skips the prediction,
+ * want_nll == 0 skips the NLL.  ffgp_dense_nll_f64 / ffgp_dense_predict_f64 are thin wrappers over it.
+ * --------------------------------------------------------------------------------------- */
+int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const double* inv_ls, const double* amp,
+                       const double* diag_add, const double* sigma_add, const double* Ks, const double* Kss,
+                       const double* cov_offset, int n, int d, int D, int ns, int batch, int params_batched, int clamp,
+                       int want_nll, int want_grad, int full_cov, int reuse_factor,
+                       void* workspace, size_t workspace_bytes,
+                       double* out_nll, double* out_logdet, double* out_alpha,
+                       double* g_inv_ls, double* g_amp, double* g_diag, double* g_sigma,
+                       double* out_mean, double* out_cov, int* info, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Cholesky factor and triangular inverse of `batch` SPD matrices (row-major, lower).
  * Replaces torch.linalg.cholesky + L.inverse() (cigp.py:129-131, gp_computation_pack.py:108-109).
  * A [batch][n][n] (only the lower triangle is read); L, Linv [batch][n][n] (either may be NULL).
