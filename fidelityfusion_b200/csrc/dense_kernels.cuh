@@ -183,13 +183,18 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
   const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
   A += b * sbatch; L += b * sbatch; M += b * sbatch;
 #define TT(i, k) T[(i) * BASE_LD + (k)]
+  // block load: every element is an independent 8-byte cp.async (all in flight at once; a plain load loop
+  // serialises 64 global-memory latencies per thread on the single resident CTA)
   for (int e = tid; e < BASE_N * BASE_N; e += 256) {
     const int i = e >> 7, k = e & 127;
     if (k <= i) {
-      TT(i, k) = A[(long long)i * ld + k];
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&TT(i, k));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(A + (long long)i * ld + k));
       TT(k, i + 1) = (i == k) ? 1.0 : 0.0;
     }
   }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
   int fail_col = -1;
   for (int j0 = 0; j0 < BASE_N; j0 += 8) {
     __syncthreads();
@@ -258,26 +263,34 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int v = lane + 32 * q;
+      const int isR = (v < r0) ? 1 : 0;            // running inverse (row block of the panel) vs panel rows of L
 #pragma unroll
       for (int kk = 0; kk < 8; kk++) {
-        double x;
-        if (v < r0) x = (v <= j0 + kk) ? TT(v, j0 + kk + 1) : 0.0;     // running inverse, row block of the panel
-        else x = TT(v, j0 + kk);                                          // panel rows of L
+        double x = TT(v, j0 + kk + isR);
+        if (isR && v > j0 + kk) x = 0.0;
         bv[kk][q] = x;
       }
     }
     auto do_quad = [&](int rq) {
       const int i0 = r0 + 4 * rq;
       double cacc[4][4];
+      // current values first (loads in flight during the FMA loop), accumulate the update straight into them
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int q = 0; q < 4; q++) {
+        const int v = lane + 32 * q;
 #pragma unroll
-        for (int q = 0; q < 4; q++) cacc[a][q] = 0.0;
+        for (int a = 0; a < 4; a++) {
+          double c0 = 0.0;
+          if (v < r0) c0 = TT(v, i0 + a + 1);
+          else if (v <= i0 + a) c0 = TT(i0 + a, v);
+          cacc[a][q] = c0;
+        }
+      }
 #pragma unroll
       for (int kk = 0; kk < 8; kk++) {
         double av[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++) av[a] = TT(i0 + a, j0 + kk);
+        for (int a = 0; a < 4; a++) av[a] = -TT(i0 + a, j0 + kk);
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -288,16 +301,16 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
         const int v = lane + 32 * q;
         if (v < r0) {
 #pragma unroll
-          for (int a = 0; a < 4; a++) TT(v, i0 + a + 1) -= cacc[a][q];
+          for (int a = 0; a < 4; a++) TT(v, i0 + a + 1) = cacc[a][q];
         } else {
 #pragma unroll
           for (int a = 0; a < 4; a++)
-            if (v <= i0 + a) TT(i0 + a, v) -= cacc[a][q];
+            if (v <= i0 + a) TT(i0 + a, v) = cacc[a][q];
         }
       }
     };
     if (warp == 0) {
-      // look-ahead: the next diagonal block (row quads 0,1) first, then its factor for the next panel
+      // look-ahead warp: ONLY the next diagonal block (row quads 0,1) and its factor for the next panel
       do_quad(0);
       if (nquad > 1) do_quad(1);
       __syncwarp();
@@ -317,9 +330,8 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
         for (int c = 0; c < 8; c++) Fnext[36 + c] = invn[c];
         Fnext[44] = (double)f;
       }
-      for (int rq = 2 + 7; rq < nquad; rq += 8) do_quad(rq);
     } else {
-      for (int rq = 2 + (warp - 1); rq < nquad; rq += 8) do_quad(rq);
+      for (int rq = 2 + (warp - 1); rq < nquad; rq += 7) do_quad(rq);
     }
   }
   __syncthreads();

@@ -247,8 +247,8 @@ inline int gemm_big_cfg() {
   static int cfg = -1;
   if (cfg < 0) {
     const char* e = getenv("FFGP_GEMM_CFG");
-    cfg = e ? atoi(e) : 0;
-    if (cfg < 0 || cfg > 3) cfg = 0;
+    cfg = e ? atoi(e) : 2;
+    if (cfg < 0 || cfg > 3) cfg = 2;
   }
   return cfg;
 }
