@@ -8,6 +8,7 @@
 #include "../../include/ffgp.h"
 #include "dense_kernels.cuh"
 #include "gemm_dmma.cuh"
+#include "gemm_tma.cuh"
 
 namespace ffgp {
 
@@ -46,6 +47,13 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// FFGP_GEMM_TMA=0 routes the 128-tile GEMMs through the older cp.async kernel (A/B comparisons only)
+static bool use_tma_gemm() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_GEMM_TMA"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
+
 static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long long sA, const double* B, int ldb,
                         long long sB, double* C, int ldc, long long sC, int M, int N, int K, double alpha, double beta,
                         int lower_only, int kmode, int batch, cudaStream_t st, int inner = 1, long long iA = 0,
@@ -55,6 +63,7 @@ static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long
   p.sA = sA; p.sB = sB; p.sC = sC; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only; p.kmode = kmode;
   p.heavy_first = 1;
   p.inner = inner; p.iA = iA; p.iB = iB; p.iC = iC;
+  const int batch_outer = batch;
   batch *= inner;
   ++g_launches;
   bool big = (M % 128 == 0) && (N % 128 == 0);
@@ -62,6 +71,10 @@ static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long
     const long long tm = M / 128, tn = N / 128;
     const long long tiles = (lower_only ? tm * (tm + 1) / 2 : tm * tn) * batch;
     if (tiles < (long long)num_sms()) big = false;     // 64x64 tiles: 4x the CTAs for the small levels
+  }
+  if (big && use_tma_gemm()) {
+    const cudaError_t e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st);
+    if (e != cudaErrorNotSupported) return e;
   }
   if (a_kmaj && b_kmaj) return launch_gemm<true, true>(p, batch, big, st);
   if (a_kmaj && !b_kmaj) return launch_gemm<true, false>(p, batch, big, st);

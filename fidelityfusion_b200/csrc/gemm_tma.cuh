@@ -1,0 +1,331 @@
+// Warp-specialised FP64 tensor-pipe GEMM for sm_100a: TMA-staged operand panels, mbarrier ring, DMMA consumers.
+//
+// Why (profiles/r01_ncu_gemm_v2_stalls.txt): the cp.async kernel in gemm_dmma.cuh kept the DMMA pipe 87 % busy - every
+// k-block all eight MMA warps met at one __syncthreads and then spent ~200 issue slots each on cp.async address
+// arithmetic while the pipe drained.  Here the MMA warps never compute a global address and never meet at a CTA
+// barrier:
+//   * warp 8 (one elected lane of the producer warpgroup) is the producer: per k-block it waits for the stage's `empty` mbarrier, posts the
+//     byte count on the `full` mbarrier and issues two cp.async.bulk.tensor (TMA) loads - one 128 x 16 panel of A,
+//     one of B - which land in shared memory in a bank-conflict-free layout chosen by the tensor map:
+//       k-major operand  (p contiguous):  4-D map (k, row, inner batch, outer batch), box 16 x 128, SWIZZLE_128B
+//       m-major operand  (row contiguous): 5-D "panel view" (row%8, k, row/8, inner, outer) with strides
+//                                          (8, ld*8, 64, ..) bytes, box 8 x 16 x 16 -> smem [16 panels][16 k][8 rows]
+//     so every m8n8k4 fragment load (8 rows x 4 k) touches 256 contiguous-in-bank bytes = 2 wavefronts, the minimum;
+//   * warps 0-7 (2 x 4, warp tile 64 x 32 = 32 DMMA per k4 step) wait on `full`, keep fragments double-buffered in
+//     registers one k4 step ahead (the wait for the next stage hides behind 32 DMMAs) and release the stage with one
+//     mbarrier arrive per warp.
+// 6 stages x 32 KB.  One tile per CTA, heavy tiles first: the hardware CTA scheduler is the load balancer and leaves
+// SMs to the high-priority look-ahead stream as tiles retire (a persistent grid would starve it).
+// FP64 has no tcgen05/TMEM path on sm_100a: DMMA.8x8x4 (mma.sync.m8n8k4.f64) with register operands is the FP64
+// tensor pipe; TMA + mbarrier are the Blackwell/Hopper pieces that apply.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gemm_dmma.cuh"
+
+namespace ffgp {
+
+constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 16, TG_STAGES = 6;
+constexpr int TG_CONSUMER_WARPS = 8;
+constexpr int TG_THREADS = (TG_CONSUMER_WARPS + 4) * 32;             // 2 consumer warpgroups + 1 producer warpgroup
+// Registers are a per-SM-sub-partition resource (16384 each): 12 warps launch with <= 168 registers per thread, then
+// setmaxnreg moves the producer warpgroup's share to the MMA warps (40 / 232), which need 128 accumulator registers
+// plus two fragment buffers.
+constexpr int TG_REGS_PRODUCER = 40, TG_REGS_CONSUMER = 232;
+constexpr int TG_PANEL_BYTES = TG_BM * TG_BK * 8;                       // 16 KB per operand per stage
+constexpr int TG_STAGE_BYTES = 2 * TG_PANEL_BYTES;
+constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+
+struct TmaGemmParams {
+  double* C;
+  int ldc;
+  long long sC, iC;
+  int M, N, K, inner;
+  double alpha, beta;
+  int lower_only, kmode, heavy_first;
+};
+
+__device__ __forceinline__ uint32_t tg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tg_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void tg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tg_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trap, never as a hung GPU.
+__device__ __forceinline__ void tg_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  if (done) return;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tg_tma_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3,%4,%5,%6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tg_tma_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3,%4,%5,%6,%7}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ double tg_lds(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// A_KMAJ: A(i,p) = A[i*lda + p]  else  A(i,p) = A[p*lda + i];   B_KMAJ: B(p,j) = B[j*ldb + p]  else  B[p*ldb + j]
+template <bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaGemmParams p) {
+  extern __shared__ unsigned char tg_smem_raw[];
+  const uint32_t smem_base = (tg_smem_u32(tg_smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B panels need 1024-B alignment
+  const uint32_t bar_base = smem_base + TG_STAGES * TG_STAGE_BYTES;           // full[s] at +8s, empty[s] at +64+8s
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- tile coordinates (same ordering rules as gemm_dmma_kernel) ------------------------------
+  const int tiles_m = p.M / TG_BM, tiles_n = p.N / TG_BN;
+  int t = blockIdx.x, ti, tj;
+  if (p.lower_only) {
+    const int total = tiles_m * (tiles_m + 1) / 2;
+    if (p.heavy_first && p.kmode != K_GE_ROW) t = total - 1 - t;
+    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    const int total = tiles_m * tiles_n;
+    if (p.heavy_first && (p.kmode == K_LE_ROW || p.kmode == K_LE_COL)) t = total - 1 - t;
+    if (p.kmode == K_LE_COL || p.kmode == K_GE_COL) { tj = t / tiles_m; ti = t - tj * tiles_m; }
+    else { ti = t / tiles_n; tj = t - ti * tiles_n; }
+  }
+  const int i0 = ti * TG_BM, j0 = tj * TG_BN;
+  int k_lo = 0, k_hi = p.K;
+  if (p.kmode == K_LE_ROW) k_hi = min(p.K, i0 + TG_BM);
+  else if (p.kmode == K_LE_COL) k_hi = min(p.K, j0 + TG_BN);
+  else if (p.kmode == K_GE_COL) k_lo = j0;
+  else if (p.kmode == K_GE_ROW) k_lo = i0;
+  const int KT = (k_hi - k_lo) / TG_BK;
+  const int zo = blockIdx.z / p.inner, zi = blockIdx.z - zo * p.inner;
+
+  if (tid == 0) {
+    for (int s = 0; s < TG_STAGES; s++) {
+      tg_mbar_init(bar_base + 8 * s, 1);                           // full: one arrive.expect_tx by the producer
+      tg_mbar_init(bar_base + 64 + 8 * s, TG_CONSUMER_WARPS);      // empty: one arrive per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= TG_CONSUMER_WARPS) {
+    // ===================== TMA producer warpgroup (one elected lane works) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TG_REGS_PRODUCER));
+    if (warp == TG_CONSUMER_WARPS && lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      for (int kt = 0; kt < KT; kt++) {
+        const int s = kt % TG_STAGES;
+        const uint32_t full = bar_base + 8 * s, empty = bar_base + 64 + 8 * s;
+        if (kt >= TG_STAGES) tg_mbar_wait(empty, ((kt / TG_STAGES) - 1) & 1);
+        tg_mbar_expect_tx(full, TG_STAGE_BYTES);
+        const uint32_t dstA = smem_base + s * TG_STAGE_BYTES, dstB = dstA + TG_PANEL_BYTES;
+        const int k0 = k_lo + kt * TG_BK;
+        if (A_KMAJ) tg_tma_4d(dstA, &mapA, full, k0, i0, zi, zo);
+        else tg_tma_5d(dstA, &mapA, full, 0, k0, i0 >> 3, zi, zo);
+        if (B_KMAJ) tg_tma_4d(dstB, &mapB, full, k0, j0, zi, zo);
+        else tg_tma_5d(dstB, &mapB, full, 0, k0, j0 >> 3, zi, zo);
+      }
+    }
+    return;
+  }
+
+  // ===================== DMMA consumers =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TG_REGS_CONSUMER));
+  const int wm = warp >> 2, wn = warp & 3;                 // 2 x 4 warps, warp tile 64 x 32
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr int MT = 8, NT = 4;
+  double* __restrict__ Cg = p.C + (long long)zo * p.sC + (long long)zi * p.iC;
+  const double alpha = p.alpha, beta = p.beta;
+
+  double acc[MT][NT][2];
+  const bool init_from_c = (beta != 0.0) && (alpha != 0.0);
+  if (init_from_c) {
+    // C is read while the first panels are in flight: acc starts at (beta/alpha) C, the epilogue multiplies by alpha
+    const double r = beta / alpha;
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+      const int row = i0 + wm * 64 + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        const int col = j0 + wn * 32 + j * 8 + tq * 2;
+        const double2 o = *reinterpret_cast<const double2*>(Cg + (long long)row * p.ldc + col);
+        acc[i][j][0] = r * o.x;
+        acc[i][j][1] = r * o.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+      for (int j = 0; j < NT; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  }
+
+  // per-thread fragment offsets inside a stage (bytes)
+  const uint32_t swz_h = (uint32_t)((tq >> 1) ^ g);        // k-major: 16-B chunk index = (2 kk + (tq>>1)) ^ (row & 7)
+  const uint32_t a_off = A_KMAJ ? (uint32_t)((wm * 64 + g) * 128 + ((tq & 1) << 3))
+                                : (uint32_t)(wm * 8 * 1024 + tq * 64 + g * 8);
+  const uint32_t b_off = TG_PANEL_BYTES + (B_KMAJ ? (uint32_t)((wn * 32 + g) * 128 + ((tq & 1) << 3))
+                                                  : (uint32_t)(wn * 4 * 1024 + tq * 64 + g * 8));
+  double af[2][MT], bf[2][NT];
+  auto load_frags = [&](int buf, uint32_t stage_base, int kk) {
+    const uint32_t kx = A_KMAJ || B_KMAJ ? (((uint32_t)(2 * kk) ^ swz_h) << 4) : 0u;
+    const uint32_t pa = stage_base + a_off + (A_KMAJ ? kx : (uint32_t)(kk * 256));
+    const uint32_t pb = stage_base + b_off + (B_KMAJ ? kx : (uint32_t)(kk * 256));
+#pragma unroll
+    for (int i = 0; i < MT; i++) af[buf][i] = tg_lds(pa + i * 1024);
+#pragma unroll
+    for (int j = 0; j < NT; j++) bf[buf][j] = tg_lds(pb + j * 1024);
+  };
+
+  if (KT > 0) {
+    tg_mbar_wait(bar_base, 0);
+    load_frags(0, smem_base, 0);
+  }
+  for (int kt = 0; kt < KT; kt++) {
+    const int s = kt % TG_STAGES;
+    const uint32_t stage_base = smem_base + s * TG_STAGE_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < TG_BK / 4; kk++) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk < TG_BK / 4 - 1) {
+        load_frags(nxt, stage_base, kk + 1);
+      } else if (kt + 1 < KT) {
+        const int s2 = (kt + 1) % TG_STAGES;
+        tg_mbar_wait(bar_base + 8 * s2, ((kt + 1) / TG_STAGES) & 1);
+        load_frags(nxt, smem_base + s2 * TG_STAGE_BYTES, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < MT; i++)
+#pragma unroll
+        for (int j = 0; j < NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+      if (kk == TG_BK / 4 - 2) {
+        // the last fragments of this stage are in registers: hand the stage back to the producer
+        __syncwarp();
+        if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s);
+      }
+    }
+  }
+
+  // ---- epilogue: C fragment (row g, cols 2 tq, 2 tq + 1) -> 16-byte stores ----------------------
+#pragma unroll
+  for (int i = 0; i < MT; i++) {
+    const int row = i0 + wm * 64 + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int col = j0 + wn * 32 + j * 8 + tq * 2;
+      double2* dst = reinterpret_cast<double2*>(Cg + (long long)row * p.ldc + col);
+      double2 v;
+      if (init_from_c || beta == 0.0) {
+        v.x = alpha * acc[i][j][0];
+        v.y = alpha * acc[i][j][1];
+      } else {                                  // alpha == 0, beta != 0
+        const double2 o = *dst;
+        v.x = beta * o.x;
+        v.y = beta * o.y;
+      }
+      *dst = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: tensor-map encoding (driver entry point fetched through the runtime, no libcuda link) and launch.
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*TgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline TgEncodeFn tg_encode_fn() {
+  static TgEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (TgEncodeFn)f;
+  }
+  return fn;
+}
+
+// rows x K operand with row/col layout flag, leading dimension ld, two batch levels (inner count/stride, outer
+// count/stride; strides in elements).  Returns false when the operand cannot be described (caller falls back).
+inline bool tg_make_map(CUtensorMap* map, const double* base, bool kmaj, int rows, int K, int ld, int inner,
+                        long long istride, int outer, long long ostride) {
+  TgEncodeFn enc = tg_encode_fn();
+  if (!enc) return false;
+  if (((uintptr_t)base & 15) || (ld & 1)) return false;
+  if ((inner > 1 && (istride <= 0 || (istride & 1))) || (outer > 1 && (ostride <= 0 || (ostride & 1)))) return false;
+  const cuuint64_t ib = (inner > 1 ? (cuuint64_t)istride : 2) * 8, ob = (outer > 1 ? (cuuint64_t)ostride : 2) * 8;
+  CUresult r;
+  if (kmaj) {
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 8, ib, ob};
+    cuuint32_t box[4] = {(cuuint32_t)TG_BK, (cuuint32_t)TG_BM, 1, 1}, es[4] = {1, 1, 1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[5] = {8, (cuuint64_t)K, (cuuint64_t)(rows / 8), (cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[4] = {(cuuint64_t)ld * 8, 64, ib, ob};
+    cuuint32_t box[5] = {8, (cuuint32_t)TG_BK, (cuuint32_t)(TG_BM / 8), 1, 1}, es[5] = {1, 1, 1, 1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  return r == CUDA_SUCCESS;
+}
+
+template <bool A_KMAJ, bool B_KMAJ>
+cudaError_t launch_gemm_tma_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TmaGemmParams& tp, int tiles, int batch,
+                                cudaStream_t st) {
+  auto kern = gemm_tma_kernel<A_KMAJ, B_KMAJ>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<dim3(tiles, 1, batch), TG_THREADS, TG_SMEM_BYTES, st>>>(mA, mB, tp);
+  return cudaGetLastError();
+}
+
+// Returns cudaErrorNotSupported when the problem cannot go through the TMA kernel (caller uses gemm_dmma_kernel).
+inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p, int batch_outer, cudaStream_t st) {
+  if (p.M % TG_BM || p.N % TG_BN || p.K % TG_BK || p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorNotSupported;
+  if (((uintptr_t)p.C & 15) || (p.ldc & 1)) return cudaErrorNotSupported;
+  CUtensorMap mA, mB;
+  if (!tg_make_map(&mA, p.A, a_kmaj, p.M, p.K, p.lda, p.inner, p.iA, batch_outer, p.sA)) return cudaErrorNotSupported;
+  if (!tg_make_map(&mB, p.B, b_kmaj, p.N, p.K, p.ldb, p.inner, p.iB, batch_outer, p.sB)) return cudaErrorNotSupported;
+  TmaGemmParams tp;
+  tp.C = p.C; tp.ldc = p.ldc; tp.sC = p.sC; tp.iC = p.iC; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.inner = p.inner;
+  tp.alpha = p.alpha; tp.beta = p.beta; tp.lower_only = p.lower_only; tp.kmode = p.kmode; tp.heavy_first = p.heavy_first;
+  const int tm = p.M / TG_BM, tn = p.N / TG_BN;
+  const int tiles = p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  const int batch = batch_outer * p.inner;
+  if (a_kmaj && b_kmaj) return launch_gemm_tma_cfg<true, true>(mA, mB, tp, tiles, batch, st);
+  if (a_kmaj && !b_kmaj) return launch_gemm_tma_cfg<true, false>(mA, mB, tp, tiles, batch, st);
+  if (!a_kmaj && b_kmaj) return launch_gemm_tma_cfg<false, true>(mA, mB, tp, tiles, batch, st);
+  return launch_gemm_tma_cfg<false, false>(mA, mB, tp, tiles, batch, st);
+}
+
+}  // namespace ffgp
