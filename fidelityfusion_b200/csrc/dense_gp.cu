@@ -332,6 +332,14 @@ static cudaError_t trtri_bottom_up(const FactorCtx& c, int np) {
   return cudaSuccess;
 }
 
+// FFGP_DEBUG_STOP_AFTER=1|2|3 truncates an evaluation after potrf | trtri | the S = M^T M product (results are then
+// meaningless): profiling aid for tools/phase_times.py, never set in production.
+static int debug_stop_after() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_DEBUG_STOP_AFTER"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 static bool g_attr_done = false;
 static cudaError_t ensure_attrs() {
   if (g_attr_done) return cudaSuccess;
@@ -375,6 +383,7 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};
   // look-ahead needs spare SMs: with a large batch every launch already fills the machine
   FFGP_CUDA(potrf_right_looking(c, w.np, /*lookahead=*/nb < 8));
+  if (debug_stop_after() == 1) return 0;              // tools/phase_times.py: time the phases separately
   FFGP_CUDA(trtri_bottom_up(c, w.np));
   return 0;
 }
@@ -496,6 +505,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
     int rc;
     if (!reuse_factor) {
       if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
+      if (debug_stop_after() == 1 || debug_stop_after() == 2) continue;
       if ((rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
     }
     if (want_nll) {
@@ -507,6 +517,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
     if (want_grad) {
       // S = M^T M (lower) into the dead A buffer
       FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
+      if (debug_stop_after() == 3) continue;
       int src_is_G = 0;
       if (w.gemm_rhs) {   // G = 0.5 (D S - alpha alpha^T) through the GEMM epilogue
         const long long sG = (long long)w.np * w.Dp;

@@ -139,15 +139,32 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixPa
 // inverse), so potrf and trtri share every pass over shared memory.
 // smem T[128][129]: T[i][k], k<=i holds A/L; T[c][i+1], c<=i holds R[i][c] (running inverse).
 // The odd row stride makes both row-wise and column-wise warp accesses bank-conflict free.
-// Per 8-column panel:  (a) the 8x8 diagonal factor is NOT on the critical path: warp 0 updates the next
-// diagonal block first and factors it (every lane redundantly, in registers) while the other warps finish the
-// rank-8 update (look-ahead inside the CTA);  (b) one thread per row solves the panel / one per column scales
-// the inverse's row block;  (c) rank-8 update with a warp per 4-row group: the row operand is a broadcast, the
-// column operand (8 x 128, shared by every row group) is hoisted into registers once per panel.
+//
+// This kernel sits on the critical path of the blocked Cholesky (one CTA, everything else waits for it), and what
+// bounds it is the dependent chain  rsqrt -> scale -> update -> rsqrt  of the 128 pivots (about 150 clk per column),
+// so the work is split by role (profiles/r01_base_kernel_timeline.txt: the previous version, where every warp did a
+// share of everything behind divergent branches, needed 8400 clk per 8-column panel; 2000 is the chain):
+//   warp 0      the critical chain of panel p+1 only: panel solve of the 8 rows of the next diagonal block, their
+//               rank-8 update of that 8x8 block, its Cholesky in registers (every lane redundantly - no exchange on
+//               the chain), publish the factor for the next iteration;
+//   warps 1-7   everything off the chain for panel p: panel solve of the remaining rows and of the inverse's row
+//               block (one thread per row / column), then the rank-8 update of the trailing matrix and of the running
+//               inverse (a warp per 4-row group, lane owns 4 "virtual columns": v < r0 inverse, v >= r0 matrix).
+// One CTA barrier per panel plus one producer/consumer named barrier (warp 0 arrives after its panel rows are stored,
+// warps 1-7 wait before the update).  All loads are unconditional with selected addresses and all masked stores go
+// to a dummy word: no divergent branches in the loop.
 // ------------------------------------------------------------------------------------------
 constexpr int BASE_N = 128;
 constexpr int BASE_LD = 129;
-constexpr size_t BASE_SMEM = ((size_t)BASE_N * BASE_LD + 48 + 64) * sizeof(double);
+constexpr int BASE_F = 48;                                   // 36 factor entries + 8 inverses + fail column (+pad)
+constexpr size_t BASE_SMEM = ((size_t)BASE_N * BASE_LD + 2 * BASE_F + 64 + 64 + 8) * sizeof(double);
+
+#ifdef FFGP_BASE_TRACE
+__device__ long long g_base_trace[8 * 16 * 4];          // [warp][panel][slot] clock64 stamps (tools/base_trace.cu)
+#define BASE_STAMP(panel, slot) do { if (lane == 0) g_base_trace[(warp * 16 + (panel)) * 4 + (slot)] = clock64(); } while (0)
+#else
+#define BASE_STAMP(panel, slot) do { } while (0)
+#endif
 
 // Cholesky of an 8x8 block held in registers (lower part of l), returns first failing column or -1.
 __device__ __forceinline__ int chol8_regs(double (&l)[8][8], double (&inv)[8]) {
@@ -173,13 +190,18 @@ __device__ __forceinline__ int chol8_regs(double (&l)[8][8], double (&inv)[8]) {
   return fail;
 }
 
+__device__ __forceinline__ void base_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void base_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
     const double* __restrict__ A, double* __restrict__ L, double* __restrict__ M, int ld, long long sbatch,
     double* __restrict__ logdet_part, int logdet_stride, int blk, int* __restrict__ info, int row_offset) {
   extern __shared__ __align__(16) double sm[];
   double* T = sm;                                   // [128][129]
-  double* Fnext = sm + BASE_N * BASE_LD;            // 36 factor entries + 8 inverses + fail column
-  double* red = Fnext + 48;
+  double* F = sm + BASE_N * BASE_LD;                // [2][BASE_F] published diagonal factors (double-buffered)
+  double* Dn = F + 2 * BASE_F;                      // [36] updated next diagonal block (warp 0 scratch)
+  double* red = Dn + 64;
+  const int DUMMY = BASE_N * BASE_LD + 2 * BASE_F + 128;   // sink for masked stores
   const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
   A += b * sbatch; L += b * sbatch; M += b * sbatch;
 #define TT(i, k) T[(i) * BASE_LD + (k)]
@@ -195,36 +217,62 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
   }
   asm volatile("cp.async.commit_group;\n" ::);
   asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
   int fail_col = -1;
-  for (int j0 = 0; j0 < BASE_N; j0 += 8) {
+  double l[8][8], inv[8];
+  {  // factor of the first diagonal block: every thread redundantly, thread 0 stores it
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int c = 0; c <= r; c++) l[r][c] = TT(r, c);
+    const int f = chol8_regs(l, inv);
+    if (f >= 0) fail_col = f;
     __syncthreads();
-    double l[8][8], inv[8];
-    if (j0 == 0) {
+    if (tid == 0) {
 #pragma unroll
       for (int r = 0; r < 8; r++)
 #pragma unroll
-        for (int c = 0; c <= r; c++) l[r][c] = TT(r, c);
-      const int f = chol8_regs(l, inv);
-      if (f >= 0 && fail_col < 0) fail_col = f;
-      __syncthreads();                               // everyone has read the block before (b) overwrites it
-    } else {
+        for (int c = 0; c <= r; c++) TT(r, c) = l[r][c];
+    }
+  }
+  // warp 0: (row, col) of the next-diagonal-block entries a lane updates (entry e and, for the tail, entry 32 + e % 4)
+  int ea0, eb0, ea1, eb1;
+  {
+    auto decode = [](int e, int& a, int& bb) {
+      a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      if (a * (a + 1) / 2 > e) --a;
+      if ((a + 1) * (a + 2) / 2 <= e) ++a;
+      bb = e - a * (a + 1) / 2;
+    };
+    decode(lane, ea0, eb0);
+    decode(32 + (lane & 3), ea1, eb1);
+  }
+  for (int p = 0; p < BASE_N / 8; p++) {
+    const int j0 = p * 8, r0 = j0 + 8;
+    if (p > 0) {
+      __syncthreads();
+    }
+    if (p > 0 && warp != 0) {                       // warp 0 carries the factor it computed in registers
+      const double* Fp = F + (p & 1) * BASE_F;
       int q = 0;
 #pragma unroll
       for (int r = 0; r < 8; r++)
 #pragma unroll
-        for (int c = 0; c <= r; c++) l[r][c] = Fnext[q++];
+        for (int c = 0; c <= r; c++) l[r][c] = Fp[q++];
 #pragma unroll
-      for (int c = 0; c < 8; c++) inv[c] = Fnext[36 + c];
-      const int f = (int)Fnext[44];
+      for (int c = 0; c < 8; c++) inv[c] = Fp[36 + c];
+      const int f = (int)Fp[44];
       if (f >= 0 && fail_col < 0) fail_col = j0 + f;
     }
-    // (b) panel rows: a <- a L11^-T ; inverse row block: v <- L11^-1 v
-    if (tid < 128) {
-      const int r = tid;
-      if (r >= j0) {
+    BASE_STAMP(p, 0);
+    if (warp == 0) {
+      if (r0 == BASE_N) continue;                  // last panel: nothing below it
+      // ---- W0.1: panel solve of the rows of the NEXT diagonal block:  a <- a L11^-T ----
+      if (lane < 8) {
+        const int r = r0 + lane;
         double a[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) a[c] = (j0 + c <= r) ? TT(r, j0 + c) : 0.0;
+        for (int c = 0; c < 8; c++) a[c] = TT(r, j0 + c);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
           double v = a[c];
@@ -233,57 +281,135 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
           a[c] = v * inv[c];
         }
 #pragma unroll
-        for (int c = 0; c < 8; c++)
-          if (j0 + c <= r) TT(r, j0 + c) = a[c];
+        for (int c = 0; c < 8; c++) TT(r, j0 + c) = a[c];
       }
-    } else {
-      const int c = tid - 128;
-      if (c < j0 + 8) {
-        double v[8];
+      __syncwarp();
+      __threadfence_block();
+      base_bar_arrive(1, 256);                     // warps 1-7 may now read these 8 panel rows
+      BASE_STAMP(p, 1);
+      // ---- W0.2: rank-8 update of the next 8x8 diagonal block: lane e owns entry e, lanes 0-3 also entry 32+e
+      //      (the other lanes recompute entry e there, harmlessly, so the two chains interleave without divergence) ----
+      {
+        double d0 = TT(r0 + ea0, r0 + eb0), d1 = TT(r0 + ea1, r0 + eb1);
+        const double* pa0 = T + (r0 + ea0) * BASE_LD + j0;
+        const double* pb0 = T + (r0 + eb0) * BASE_LD + j0;
+        const double* pa1 = T + (r0 + ea1) * BASE_LD + j0;
+        const double* pb1 = T + (r0 + eb1) * BASE_LD + j0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (c <= j0 + k) ? TT(c, j0 + k + 1) : 0.0;
+        for (int kk = 0; kk < 8; kk++) {
+          d0 = fma(-pa0[kk], pb0[kk], d0);
+          d1 = fma(-pa1[kk], pb1[kk], d1);
+        }
+        Dn[lane] = d0;
+        Dn[32 + (lane & 3)] = d1;                  // lanes sharing (lane & 3) write identical values
+      }
+      __syncwarp();
+      BASE_STAMP(p, 2);
+      // ---- W0.3: its Cholesky, every lane redundantly in registers; publish for the next iteration ----
+      {
+        int q = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          double u = v[k];
+        for (int r = 0; r < 8; r++)
 #pragma unroll
-          for (int q = 0; q < k; q++) u = fma(-l[k][q], v[q], u);
-          v[k] = u * inv[k];
+          for (int c = 0; c <= r; c++) l[r][c] = Dn[q++];
+      }
+      const int f = chol8_regs(l, inv);
+      if (f >= 0 && fail_col < 0) fail_col = r0 + f;
+      double* Fn = F + ((p + 1) & 1) * BASE_F;
+      if (lane == 0) {
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int c = 0; c <= r; c++) Fn[q++] = l[r][c];
+#pragma unroll
+        for (int c = 0; c < 8; c++) Fn[36 + c] = inv[c];
+        Fn[44] = (double)f;
+      } else if (lane == 1) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int c = 0; c <= r; c++) TT(r0 + r, r0 + c) = l[r][c];
+      }
+      BASE_STAMP(p, 3);
+      continue;
+    }
+    // =============================== warps 1-7 ===============================
+    // ---- O.1: panel solve, one item per thread: rows below the next diagonal block, then the inverse's columns ----
+    {
+      const int item = tid - 32;
+      const int nrows = BASE_N - r0 - 8;           // rows r0+8 .. 127  (may be <= 0)
+      if (item < nrows) {
+        const int r = r0 + 8 + item;
+        double a[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) a[c] = TT(r, j0 + c);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          double v = a[c];
+#pragma unroll
+          for (int k = 0; k < c; k++) v = fma(-a[k], l[c][k], v);
+          a[c] = v * inv[c];
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (c <= j0 + k) TT(c, j0 + k + 1) = v[k];
+        for (int c = 0; c < 8; c++) TT(r, j0 + c) = a[c];
+      } else {
+        const int c = item - max(nrows, 0);
+        if (c < j0 + 8) {                          // inverse row block: v <- L11^-1 v   (column c of rows j0..j0+7)
+          double v[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const double x = TT(c, j0 + k + 1);
+            v[k] = (c <= j0 + k) ? x : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            double u = v[k];
+#pragma unroll
+            for (int q = 0; q < k; q++) u = fma(-l[k][q], v[q], u);
+            v[k] = u * inv[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int idx = (c <= j0 + k) ? c * BASE_LD + j0 + k + 1 : DUMMY;
+            T[idx] = v[k];
+          }
+        }
       }
     }
-    __syncthreads();
-    // (c) rank-8 update of the rows below the panel.  Lane owns virtual columns v = lane + 32 q.
-    const int r0 = j0 + 8;
+    if (r0 == BASE_N) continue;
+    base_bar_sync(1, 256);
+    BASE_STAMP(p, 1);
+    // ---- O.2: rank-8 update of the rows below the panel.  Lane owns virtual columns v = lane + 32 q. ----
     const int nquad = (BASE_N - r0) >> 2;
-    if (nquad == 0) continue;
     double bv[8][4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int v = lane + 32 * q;
       const int isR = (v < r0) ? 1 : 0;            // running inverse (row block of the panel) vs panel rows of L
+      const double* src = T + v * BASE_LD + j0 + isR;
 #pragma unroll
       for (int kk = 0; kk < 8; kk++) {
-        double x = TT(v, j0 + kk + isR);
-        if (isR && v > j0 + kk) x = 0.0;
-        bv[kk][q] = x;
+        const double x = src[kk];
+        bv[kk][q] = (isR && v > j0 + kk) ? 0.0 : x;
       }
     }
-    auto do_quad = [&](int rq) {
+    BASE_STAMP(p, 2);
+    for (int rq = warp - 1; rq < nquad; rq += 7) {
       const int i0 = r0 + 4 * rq;
       double cacc[4][4];
-      // current values first (loads in flight during the FMA loop), accumulate the update straight into them
+      int idx[4][4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int v = lane + 32 * q;
+        const bool isR = v < r0;
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-          double c0 = 0.0;
-          if (v < r0) c0 = TT(v, i0 + a + 1);
-          else if (v <= i0 + a) c0 = TT(i0 + a, v);
-          cacc[a][q] = c0;
+          const int i = i0 + a;
+          const int id = isR ? v * BASE_LD + i + 1 : i * BASE_LD + min(v, i);
+          cacc[a][q] = T[id];
+          // the 8x8 block on the diagonal right after the panel belongs to warp 0; entries above the diagonal do not exist
+          idx[a][q] = (isR || (v <= i && i >= r0 + 8)) ? id : DUMMY;
         }
       }
 #pragma unroll
@@ -297,42 +423,11 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
           for (int q = 0; q < 4; q++) cacc[a][q] = fma(av[a], bv[kk][q], cacc[a][q]);
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int v = lane + 32 * q;
-        if (v < r0) {
+      for (int q = 0; q < 4; q++)
 #pragma unroll
-          for (int a = 0; a < 4; a++) TT(v, i0 + a + 1) = cacc[a][q];
-        } else {
-#pragma unroll
-          for (int a = 0; a < 4; a++)
-            if (v <= i0 + a) TT(i0 + a, v) = cacc[a][q];
-        }
-      }
-    };
-    if (warp == 0) {
-      // look-ahead warp: ONLY the next diagonal block (row quads 0,1) and its factor for the next panel
-      do_quad(0);
-      if (nquad > 1) do_quad(1);
-      __syncwarp();
-      double ln[8][8], invn[8];
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int c = 0; c <= r; c++) ln[r][c] = TT(r0 + r, r0 + c);
-      const int f = chol8_regs(ln, invn);
-      if (lane == 0) {
-        int q = 0;
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-          for (int c = 0; c <= r; c++) Fnext[q++] = ln[r][c];
-#pragma unroll
-        for (int c = 0; c < 8; c++) Fnext[36 + c] = invn[c];
-        Fnext[44] = (double)f;
-      }
-    } else {
-      for (int rq = 2 + (warp - 1); rq < nquad; rq += 7) do_quad(rq);
+        for (int a = 0; a < 4; a++) T[idx[a][q]] = cacc[a][q];
     }
+    BASE_STAMP(p, 3);
   }
   __syncthreads();
   for (int e = tid; e < BASE_N * BASE_N; e += 256) {
@@ -347,8 +442,9 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
     double s = 0.0;
     for (int k = 0; k < 64; k++) s += red[k];
     logdet_part[(long long)b * logdet_stride + blk] = s;
-    if (fail_col >= 0) atomicCAS(info + b, 0, row_offset + fail_col + 1);
   }
+  // every thread tracked the published fail columns identically; thread 0 reports
+  if (tid == 0 && fail_col >= 0) atomicCAS(info + b, 0, row_offset + fail_col + 1);
 #undef TT
 }
 
