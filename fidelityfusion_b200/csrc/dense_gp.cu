@@ -128,7 +128,12 @@ static DenseWs layout_ws(int n, int d, int D, int ns, int batch, char* base) {
   const size_t item = per_item();
   long long chunk = (long long)(WS_TARGET_BYTES / item);
   if (chunk < 1) chunk = 1;
-  w.chunk = (int)std::min<long long>(chunk, std::max(batch, 1));
+  {  // balanced chunks: 1024 problems with room for 1016 must not become 1016 + 8 (the tail chunk pays every launch
+     // latency of a full one, profiles/r01_metrics_c5_v1.txt)
+    const long long bt = std::max(batch, 1);
+    const long long nchunks = (bt + chunk - 1) / chunk;
+    w.chunk = (int)((bt + nchunks - 1) / nchunks);
+  }
   size_t off = 0;
   auto take = [&](size_t nbytes) {
     char* ptr = base ? base + off : nullptr;
@@ -217,8 +222,10 @@ static cudaError_t factor_rec(const FactorCtx& c, int off, int n) {
 //   3. (gradient) S = M^T M, one launch.
 // ---------------------------------------------------------------------------------------------
 struct AuxStream {
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+  cudaStream_t st = nullptr;        // panel chain (highest priority)
+  cudaStream_t st_bulk = nullptr;   // trailing updates of a large single factorisation (middle priority)
+  cudaStream_t st_bg = nullptr;     // background work overlapped with the chain-bound tail (lowest priority)
+  cudaEvent_t ev_main = nullptr, ev_aux = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_half = nullptr, ev_bg = nullptr;
 };
 static AuxStream g_aux[64];
 
@@ -229,10 +236,13 @@ static cudaError_t get_aux(AuxStream** out) {
   AuxStream& a = g_aux[dev & 63];
   if (!a.st) {
     int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);        // lo = least urgent (0), hi = most urgent (negative)
     if ((e = cudaStreamCreateWithPriority(&a.st, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
-    if ((e = cudaEventCreateWithFlags(&a.ev_main, cudaEventDisableTiming)) != cudaSuccess) return e;
-    if ((e = cudaEventCreateWithFlags(&a.ev_aux, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&a.st_bulk, cudaStreamNonBlocking, (lo + hi) / 2)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&a.st_bg, cudaStreamNonBlocking, lo)) != cudaSuccess) return e;
+    cudaEvent_t* evs[6] = {&a.ev_main, &a.ev_aux, &a.ev_fork, &a.ev_join, &a.ev_half, &a.ev_bg};
+    for (auto ev : evs)
+      if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
   }
   *out = &a;
   return cudaSuccess;
@@ -249,7 +259,11 @@ static int outer_nb() {
   return g_outer_nb;
 }
 
-static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahead) {
+// `at_half` (optional) is called once, right after every block column of the LEADING HALF of the matrix is final
+// (its panel factored and its rows below solved): from then on L[:, 0:np/2] and the diagonal-block inverses of the
+// leading half no longer change.
+template <class Hook>
+static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahead, Hook at_half) {
   cudaError_t e;
   int NB = outer_nb();
   if (np % NB != 0) NB = BASE_N;
@@ -293,8 +307,12 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
       if ((e = cudaEventRecord(aux->ev_aux, aux->st)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(c.st, aux->ev_aux, 0)) != cudaSuccess) return e;
     }
+    if ((k + 2) * 2 == nblk && (e = at_half()) != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahead) {
+  return potrf_right_looking(c, np, lookahead, []() { return cudaSuccess; });
 }
 
 // M21 = -M22 L21 M11 for the node [off, off+n) split at h (general, sequential; used when np/NB is not a power of 2)
@@ -330,6 +348,62 @@ static cudaError_t trtri_bottom_up(const FactorCtx& c, int np) {
                   K_GE_COL, c.batch, c.st, nodes, node_stride, node_stride, node_stride)) != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+static cudaError_t trtri_bottom_up_range(const FactorCtx& c, int off, int n) {
+  FactorCtx r = c;
+  const long long d = (long long)off * c.ld + off;
+  r.A += d; r.L += d; r.M += d;
+  return trtri_bottom_up(r, n);
+}
+
+// Single large problem: factorisation AND triangular inverse with the first half of the inverse overlapped with the
+// second half of the factorisation.  profiles/r01_launches_bench_v5.csv: from the matrix midpoint on, every
+// right-looking step is bound by its serial panel chain (diag update -> two 128-blocks -> TRSM, ~230 us) while the
+// trailing update needs less than that, so most SMs idle for ~3.6 ms at N = 8192; and the inverse
+//   M21 = -M22 L21 M11  =  -M22 (L21 M11)
+// has half of its FLOPs (inverse of the leading half, then W = L21 M11) depending only on the LEADING half of L,
+// which is final at the midpoint.  Streams: panel chain (highest priority) > trailing updates > background W.
+static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int stop_after, bool* done) {
+  *done = false;
+  int NB = outer_nb();
+  if (np % NB != 0) return cudaSuccess;
+  const int nblk = np / NB;
+  if (nblk < 8 || (nblk & (nblk - 1))) return cudaSuccess;          // needs a power-of-two block count >= 8
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("FFGP_OVERLAP"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (!enabled) return cudaSuccess;
+  cudaError_t e;
+  AuxStream* aux = nullptr;
+  if ((e = get_aux(&aux)) != cudaSuccess) return e;
+  const int h = np / 2;
+  const long long o21 = (long long)h * c.ld, o22 = (long long)h * c.ld + h;
+  // fork: the factorisation runs on the library's middle-priority stream
+  if ((e = cudaEventRecord(aux->ev_fork, c.st)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(aux->st_bulk, aux->ev_fork, 0)) != cudaSuccess) return e;
+  FactorCtx cb = c; cb.st = aux->st_bulk;
+  FactorCtx cg = c; cg.st = aux->st_bg;
+  auto at_half = [&]() -> cudaError_t {
+    if (stop_after == 1) return cudaSuccess;
+    cudaError_t e2;
+    if ((e2 = cudaEventRecord(aux->ev_half, cb.st)) != cudaSuccess) return e2;
+    if ((e2 = cudaStreamWaitEvent(cg.st, aux->ev_half, 0)) != cudaSuccess) return e2;
+    if ((e2 = trtri_bottom_up_range(cg, 0, h)) != cudaSuccess) return e2;
+    // W = L21 M11 -> A21 (dead: every block column of the leading half has been solved)
+    return gemm(true, false, c.L + o21, c.ld, c.sb, c.M, c.ld, c.sb, c.A + o21, c.ld, c.sb, h, h, h, 1.0, 0.0, 0, K_GE_COL,
+                c.batch, cg.st);
+  };
+  if ((e = potrf_right_looking(cb, np, true, at_half)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(aux->ev_join, cb.st)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(c.st, aux->ev_join, 0)) != cudaSuccess) return e;
+  *done = true;
+  if (stop_after == 1) return cudaSuccess;
+  // inverse of the trailing half, then the one product that needs both halves
+  if ((e = trtri_bottom_up_range(c, h, h)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(aux->ev_bg, cg.st)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(c.st, aux->ev_bg, 0)) != cudaSuccess) return e;
+  return gemm(true, false, c.M + o22, c.ld, c.sb, c.A + o21, c.ld, c.sb, c.M + o21, c.ld, c.sb, h, h, h, -1.0, 0.0, 0, K_LE_ROW,
+              c.batch, c.st);
 }
 
 // FFGP_DEBUG_STOP_AFTER=1|2|3 truncates an evaluation after potrf | trtri | the S = M^T M product (results are then
@@ -382,6 +456,11 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   FFGP_LAUNCHED();
   FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};
   // look-ahead needs spare SMs: with a large batch every launch already fills the machine
+  if (nb < 8) {
+    bool done = false;
+    FFGP_CUDA(factor_and_invert_overlapped(c, w.np, debug_stop_after(), &done));
+    if (done) return 0;
+  }
   FFGP_CUDA(potrf_right_looking(c, w.np, /*lookahead=*/nb < 8));
   if (debug_stop_after() == 1) return 0;              // tools/phase_times.py: time the phases separately
   FFGP_CUDA(trtri_bottom_up(c, w.np));

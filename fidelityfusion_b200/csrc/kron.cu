@@ -12,6 +12,7 @@
 #include <cstring>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 #include "../../include/ffgp.h"
 #include "gemm_dmma.cuh"
 
@@ -106,6 +107,174 @@ __global__ void __launch_bounds__(256) mode_dot_kernel(const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Streaming n-mode product for small factor matrices (I, J <= 128: every output mode of the reference's configs
+// and the N-mode of C4).  History (profiles/r01_kron_bench_v{1,2}.txt): the generic kernel above reached 10 % of HBM
+// (factor reloaded per chunk, scalar loads, div/mod per element, no overlap); a CTA-synchronous cp.async ring
+// reached 41 % at 134 MB (one __syncthreads and three 64-bit divisions per 16 KB chunk left both the DMMA pipe and
+// HBM waiting).  This version has NO CTA-level synchronisation in the loop:
+//   * the factor matrix is staged ONCE per CTA in shared memory as ms[j][k] (stride SA = 4 mod 16 doubles: the
+//     4 rows x 4 k of a half-warp fragment load hit 16 distinct bank pairs); grid.y splits J in blocks of 64;
+//   * every WARP streams its own tiles through a private 4-stage cp.async ring (16-byte copies) and synchronises
+//     with __syncwarp only; tiles are dealt round-robin over all warps of the grid, so neighbouring warps touch
+//     neighbouring 64-byte segments at the same time:
+//       LAST == false (inner even): tile = 32 k-rows x 8 generalised columns (row stride 12 doubles),
+//                                   C[j][col]: the warp loops the J/8 m-tiles;
+//       LAST == true  (inner == 1): tile = 8 rows x 32 k (row stride 36),  C[row][j]: loops the J/8 n-tiles;
+//   * generalised column -> (outer, inner) indices advance incrementally (no division in the loop);
+//   * results leave as 16-byte stores.
+// Algorithmic bytes: 8 (I + J) per generalised column + the factor.
+// ---------------------------------------------------------------------------------------------
+constexpr int MS_KB = 32, MS_STAGES = 4;
+constexpr int MS_LD_COLS = 12;            // LAST == false: [MS_KB][8 cols + 4]   (12 t + g distinct mod 16)
+constexpr int MS_LD_K = MS_KB + 4;        // LAST == true:  [8 rows][36]
+constexpr int MS_STAGE_DOUBLES = MS_KB * MS_LD_COLS;     // 384 >= 8 * 36
+constexpr int MS_WARPS = 8;
+
+struct ModeSmallParams {
+  const double* t; const double* mat; double* out;
+  long long ncols, inner;
+  int I, J, transpose_mat, Ip, Jp, SA;
+};
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(256, 2) mode_dot_small_kernel(const ModeSmallParams p) {
+  extern __shared__ __align__(16) double msm[];
+  double* ms = msm;                                         // [<= 64 rows of this CTA's J block][SA]
+  const int j0 = blockIdx.y * 64;                           // J block of this CTA (grid.y = ceil(Jp / 64))
+  const int jrows = min(64, p.Jp - j0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  double* stages = msm + (size_t)min(p.Jp, 64) * p.SA + (size_t)warp * MS_STAGES * MS_STAGE_DOUBLES;   // warp-private ring
+  const int I = p.I, J = p.J, SA = p.SA;
+  const long long inner = p.inner, ncols = p.ncols;
+  for (int e = tid; e < jrows * SA; e += 256) {
+    const int jl = e / SA, k = e - jl * SA, j = j0 + jl;
+    double v = 0.0;
+    if (j < J && k < I) v = p.transpose_mat ? p.mat[(long long)k * J + j] : p.mat[(long long)j * I + k];
+    ms[e] = v;
+  }
+  __syncthreads();                                          // the only CTA barrier
+  const int nkb = (p.Ip + MS_KB - 1) / MS_KB;
+  const int mtiles = jrows / 8;
+  const long long nblocks = (ncols + 7) >> 3;               // 8-column (LAST: 8-row) blocks
+  const long long wstride = (long long)gridDim.x * MS_WARPS;
+  const long long wb0 = (long long)blockIdx.x * MS_WARPS + warp;
+  const long long my_blocks = (nblocks > wb0) ? (nblocks - wb0 + wstride - 1) / wstride : 0;
+  const long long nq = my_blocks * nkb;
+  // per-lane generalised column of the LOAD side (advances by wstride * 8 per block) and of the STORE side
+  const long long dq = (wstride * 8) / inner, dr = (wstride * 8) - dq * inner;
+  long long lc = wb0 * 8 + (LAST ? 0 : 2 * tq), lo = LAST ? 0 : lc / inner, lci = LAST ? 0 : lc - lo * inner;   // load cursor
+  long long sc = lc, so = lo, sci = lci;                                                                        // store cursor
+  int lkb = 0;
+  long long issued = 0;
+
+  auto issue = [&]() {
+    if (issued < nq) {
+      double* st = stages + (size_t)(issued % MS_STAGES) * MS_STAGE_DOUBLES;
+      if (!LAST) {
+        const bool cok = lc < ncols;
+        const double* src = p.t + (lo * I) * inner + lci;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int kl = g + 8 * i, k = lkb * MS_KB + kl;
+          double* dst = st + kl * MS_LD_COLS + 2 * tq;
+          if (cok && k < I) cp_async16(dst, src + (long long)k * inner);
+          else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+      } else {
+        const int kv = lane & 15, k = lkb * MS_KB + 2 * kv;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int r = (lane >> 4) + 2 * i;
+          double* dst = st + r * MS_LD_K + 2 * kv;
+          if (lc + r < ncols && k < I) cp_async16(dst, p.t + (lc + r) * I + k);
+          else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+      }
+      ++issued;
+      if (++lkb == nkb) {
+        lkb = 0;
+        lc += wstride * 8;
+        if (!LAST) { lo += dq; lci += dr; if (lci >= inner) { lci -= inner; ++lo; } }
+      }
+    }
+    cp_async_commit();
+  };
+
+  for (int q = 0; q < MS_STAGES - 1; q++) issue();
+  double acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  int kb = 0;
+  const uint32_t ms_u32 = (uint32_t)__cvta_generic_to_shared(ms) + (uint32_t)((g * SA + tq) * 8);
+  const uint32_t st_u32 = (uint32_t)__cvta_generic_to_shared(stages) + (uint32_t)((LAST ? g * MS_LD_K + tq : tq * MS_LD_COLS + g) * 8);
+  const uint32_t m_stride = (uint32_t)(SA * 64);
+  constexpr uint32_t s_step = LAST ? 32u : (uint32_t)(4 * MS_LD_COLS * 8);
+  for (long long q = 0; q < nq; q++) {
+    cp_async_wait<MS_STAGES - 2>();
+    __syncwarp();                             // tile q landed for every lane; the stage of tile q-1 is free
+    issue();
+    const uint32_t s_base = st_u32 + (uint32_t)((q % MS_STAGES) * MS_STAGE_DOUBLES * 8);
+    const uint32_t m_base = ms_u32 + (uint32_t)(kb * MS_KB * 8);
+    const int ksteps = min(MS_KB, p.Ip - kb * MS_KB) >> 2;
+#pragma unroll
+    for (int ks = 0; ks < MS_KB / 4; ks++) {
+      if (ks < ksteps) {
+        const double sf = lds_f64(s_base + ks * s_step);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (i < mtiles) {
+            const double mf = lds_f64(m_base + ks * 32 + i * m_stride);
+            if (LAST) dmma884(acc[i][0], acc[i][1], sf, mf);
+            else dmma884(acc[i][0], acc[i][1], mf, sf);
+          }
+        }
+      }
+    }
+    if (++kb == nkb) {
+      kb = 0;
+      if (!LAST) {
+        if (sc < ncols) {
+          double* dst = p.out + (so * J) * inner + sci;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int j = j0 + i * 8 + g;
+            if (i < mtiles && j < J) *reinterpret_cast<double2*>(dst + (long long)j * inner) = make_double2(acc[i][0], acc[i][1]);
+          }
+        }
+        sc += wstride * 8; so += dq; sci += dr;
+        if (sci >= inner) { sci -= inner; ++so; }
+      } else {
+        const long long r = sc + g;
+        if (r < ncols) {
+          double* dst = p.out + r * J;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int j = j0 + i * 8 + tq * 2;
+            if (i < mtiles) {
+              if (!(J & 1) && j + 1 < J) *reinterpret_cast<double2*>(dst + j) = make_double2(acc[i][0], acc[i][1]);
+              else {
+                if (j < J) dst[j] = acc[i][0];
+                if (j + 1 < J) dst[j + 1] = acc[i][1];
+              }
+            }
+          }
+        }
+        sc += wstride * 8;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Mode Gram:  G[a][b] = sum_c X(a, c) * Y(b, c)  over generalised columns, X viewed [outer][Ja][inner],
 // Y viewed [outer][Jb][inner].  CTA (bx, by, bz): 64x64 block (by, bx) of G over the bz-th slice of columns;
 // slices are summed in fixed order by gram_reduce_kernel.
@@ -172,6 +341,128 @@ __global__ void __launch_bounds__(256) mode_gram_kernel(const double* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming mode Gram (replaces mode_gram_kernel for 16-byte-alignable layouts; that kernel reached 3-7 % of HBM,
+// profiles/r01_kron_bench_v1.txt).  G tile of TILE x TILE (32 or 64) per CTA, the column range split into
+// `nslices` interleaved chunk sets; X and Y stream through a 4-stage cp.async ring of 32-column chunks; the 8 warps
+// split the chunk's k-steps (TILE = 32: 8 ways, TILE = 64: 2 x 2 warp tiles x 2 ways) and are summed in a fixed
+// order at the end; slices are summed in index order by gram_reduce_kernel (deterministic, no atomics).
+//   INNER1 == false: inner even: stage = [2 TILE rows (X rows, then Y rows)][32 columns], stride 36;
+//   INNER1 == true : inner == 1: stage = [32 columns][X: TILE | Y: TILE], row stride 2 (TILE + 4) + 4.
+// ---------------------------------------------------------------------------------------------
+constexpr int GS_CH = 32, GS_STAGES = 4;
+
+template <int TILE, bool INNER1>
+__global__ void __launch_bounds__(256) mode_gram_stream_kernel(const double* __restrict__ X, const double* __restrict__ Y,
+                                                               double* __restrict__ part, long long ncols, long long inner,
+                                                               int Ja, int Jb) {
+  constexpr int SA = TILE + 4;                       // INNER1 operand width
+  constexpr int RS1 = 2 * SA + 4;                    // INNER1 row stride (= 12 mod 16)
+  constexpr int RS0 = GS_CH + 4;                     // !INNER1 row stride (= 4 mod 16)
+  constexpr int STAGE = INNER1 ? GS_CH * RS1 : 2 * TILE * RS0;
+  constexpr int WK = (TILE == 32) ? 8 : 2;
+  extern __shared__ __align__(16) double gsm2[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int wm = (TILE == 32) ? 0 : (warp & 1), wn = (TILE == 32) ? 0 : ((warp >> 1) & 1), wk = (TILE == 32) ? warp : (warp >> 2);
+  const int a0 = blockIdx.z * TILE, b0 = blockIdx.y * TILE;
+  const long long nchunks = (ncols + GS_CH - 1) / GS_CH;
+  const long long my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  auto issue = [&](long long q) {
+    if (q < my_chunks) {
+      const long long c0 = (blockIdx.x + q * gridDim.x) * GS_CH;
+      double* st = gsm2 + (size_t)(q % GS_STAGES) * STAGE;
+      if (!INNER1) {
+        const int cv = tid & 15;
+        const long long c = c0 + 2 * cv;
+        const bool cok = c < ncols;
+        const long long o = cok ? c / inner : 0, ci = cok ? c - o * inner : 0;
+#pragma unroll
+        for (int i = 0; i < TILE / 8; i++) {
+          const int r = (tid >> 4) + 16 * i;                         // 0 .. 2 TILE - 1
+          const bool isY = r >= TILE;
+          const int row = isY ? b0 + r - TILE : a0 + r, J = isY ? Jb : Ja;
+          double* dst = st + r * RS0 + 2 * cv;
+          if (cok && row < J) cp_async16(dst, (isY ? Y : X) + (o * J + row) * inner + ci);
+          else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < TILE / 8; i++) {
+          const int v = tid + 256 * i;
+          const int vv = v % TILE, r = v / TILE;                     // TILE vectors per column row: X half, Y half
+          const bool isY = vv >= TILE / 2;
+          const int e = 2 * (vv % (TILE / 2));
+          const int J = isY ? Jb : Ja, j = (isY ? b0 : a0) + e;
+          double* dst = st + r * RS1 + (isY ? SA : 0) + e;
+          if (c0 + r < ncols && j < J) cp_async16(dst, (isY ? Y : X) + (c0 + r) * J + j);
+          else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  for (int q = 0; q < GS_STAGES - 1; q++) issue(q);
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  for (long long q = 0; q < my_chunks; q++) {
+    cp_async_wait<GS_STAGES - 2>();
+    __syncthreads();
+    issue(q + GS_STAGES - 1);
+    const double* st = gsm2 + (size_t)(q % GS_STAGES) * STAGE;
+#pragma unroll
+    for (int kq = 0; kq < GS_CH / 4 / WK; kq++) {
+      const int kc = (kq * WK + wk) * 4;
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (!INNER1) {
+          af[i] = st[(wm * 32 + i * 8 + g) * RS0 + kc + tq];
+          bf[i] = st[(TILE + wn * 32 + i * 8 + g) * RS0 + kc + tq];
+        } else {
+          af[i] = st[(kc + tq) * RS1 + wm * 32 + i * 8 + g];
+          bf[i] = st[(kc + tq) * RS1 + SA + wn * 32 + i * 8 + g];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // cross-warp sum in fixed order through shared memory: red[warp][32][34]
+  double* red = gsm2;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      double* d = red + (size_t)warp * 32 * 34 + (i * 8 + g) * 34 + j * 8 + tq * 2;
+      d[0] = acc[i][j][0];
+      d[1] = acc[i][j][1];
+    }
+  __syncthreads();
+  double* dst = part + (long long)blockIdx.x * Ja * Jb;
+  for (int e = tid; e < TILE * TILE; e += 256) {
+    const int r = e / TILE, c = e - r * TILE;
+    const int a = a0 + r, b = b0 + c;
+    if (a < Ja && b < Jb) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < WK; k++) {
+        const int wsrc = (TILE == 32) ? k : (k * 4 + (c >> 5) * 2 + (r >> 5));
+        v += red[(size_t)wsrc * 32 * 34 + (r & 31) * 34 + (c & 31)];
+      }
+      dst[(long long)a * Jb + b] = v;
+    }
+  }
+}
+
 __global__ void gram_reduce_kernel(const double* __restrict__ part, int nslices, long long nelem, double* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nelem) return;
@@ -180,10 +471,47 @@ __global__ void gram_reduce_kernel(const double* __restrict__ part, int nslices,
   out[i] = s;
 }
 
+template <int TILE, bool INNER1>
+static cudaError_t launch_gram_stream(const double* X, const double* Y, double* part, long long ncols, long long inner, int Ja,
+                                      int Jb, int ns, cudaStream_t st) {
+  constexpr int STAGE = INNER1 ? GS_CH * (2 * (TILE + 4) + 4) : 2 * TILE * (GS_CH + 4);
+  const size_t smem = std::max((size_t)GS_STAGES * STAGE, (size_t)8 * 32 * 34) * sizeof(double);
+  auto kern = mode_gram_stream_kernel<TILE, INNER1>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  kern<<<dim3(ns, (Jb + TILE - 1) / TILE, (Ja + TILE - 1) / TILE), 256, smem, st>>>(X, Y, part, ncols, inner, Ja, Jb);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kronecker core stage
 // ---------------------------------------------------------------------------------------------
 struct KronSizes { int n[8]; int off[8]; int nmodes; };
+
+// prod_{m != skip} lambda_m[i_m] of the multi-index of `idx` (row-major), with the LAST mode's factor returned
+// separately for idx and idx + 1 (pairs never straddle a last-mode row: callers use pairs only when n_last is even).
+// 32-bit index arithmetic: a 64-bit div/mod per mode per element made the first version of these kernels ALU-bound
+// (profiles/r01_kron_bench_v1.txt: kron_core at 11 % of HBM).
+__device__ __forceinline__ double kron_prefix_prod(unsigned idx, const KronSizes& s, const double* __restrict__ lam, int skip,
+                                                   unsigned& i_last) {
+  const int last = s.nmodes - 1;
+  i_last = idx % (unsigned)s.n[last];
+  idx /= (unsigned)s.n[last];
+  double p = 1.0;
+#pragma unroll
+  for (int m = 6; m >= 0; m--) {
+    if (m < last) {
+      const unsigned im = idx % (unsigned)s.n[m];
+      idx /= (unsigned)s.n[m];
+      if (m != skip) p *= lam[s.off[m] + im];
+    }
+  }
+  return p;
+}
 
 __device__ __forceinline__ double kron_lambda_prod(long long idx, const KronSizes& s, const double* __restrict__ lam, int skip) {
   double p = 1.0;
@@ -198,50 +526,101 @@ __device__ __forceinline__ double kron_lambda_prod(long long idx, const KronSize
   return p;
 }
 
+// One pass: A = kron(lambda) + tau, h = T1 / A, and the four sums (sum log A, sum T1 h, sum 1/A, sum h^2).
+// PAIRS: each thread handles element pairs with 16-byte loads/stores (total even, last mode even, total < 2^31).
+template <bool PAIRS>
 __global__ void __launch_bounds__(256) kron_core_kernel(const double* __restrict__ T1, const double* __restrict__ lam,
                                                         KronSizes s, const double* __restrict__ noise_inv, double add,
                                                         long long total, double* __restrict__ core, double* __restrict__ Aout,
                                                         double* __restrict__ part) {
-  __shared__ double red[4][256];
+  __shared__ double red[4][8];
   const double tau = (noise_inv ? noise_inv[0] : 0.0) + add;
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const double A = kron_lambda_prod(i, s, lam, -1) + tau;
-    const double t1 = T1[i];
+  auto one = [&](double A, double t1, double& h) {
     const double ia = 1.0 / A;
-    const double h = t1 * ia;
-    if (core) core[i] = h;
-    if (Aout) Aout[i] = A;
+    h = t1 * ia;
     s0 += log(A);
     s1 = fma(t1, h, s1);
     s2 += ia;
     s3 = fma(h, h, s3);
+  };
+  if (PAIRS) {
+    const int last = s.nmodes - 1;
+    const unsigned npairs = (unsigned)(total >> 1);
+    for (unsigned pi = blockIdx.x * 256u + threadIdx.x; pi < npairs; pi += gridDim.x * 256u) {
+      unsigned il;
+      const double pre = kron_prefix_prod(2u * pi, s, lam, -1, il);
+      const double2 t1 = reinterpret_cast<const double2*>(T1)[pi];
+      const double A0 = fma(pre, lam[s.off[last] + il], tau), A1 = fma(pre, lam[s.off[last] + il + 1], tau);
+      double2 h;
+      one(A0, t1.x, h.x);
+      one(A1, t1.y, h.y);
+      if (core) reinterpret_cast<double2*>(core)[pi] = h;
+      if (Aout) reinterpret_cast<double2*>(Aout)[pi] = make_double2(A0, A1);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+      const double A = kron_lambda_prod(i, s, lam, -1) + tau;
+      double h;
+      one(A, T1[i], h);
+      if (core) core[i] = h;
+      if (Aout) Aout[i] = A;
+    }
   }
-  red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2; red[3][threadIdx.x] = s3;
+  // fixed-order block reduction: warp shuffles, then 8 warp partials in index order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; red[3][warp] = s3; }
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o)
-      for (int q = 0; q < 4; q++) red[q][threadIdx.x] += red[q][threadIdx.x + o];
-    __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int k = 0; k < 8; k++) v += red[threadIdx.x][k];
+    part[(long long)blockIdx.x * 4 + threadIdx.x] = v;
   }
-  if (threadIdx.x < 4) part[(long long)blockIdx.x * 4 + threadIdx.x] = red[threadIdx.x][0];
 }
 
 __global__ void kron_sums_finish_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out) {
-  const int q = threadIdx.x;
+  // 4 warps, one per sum: lane-strided partial sums, then a shuffle tree (fixed order for a given nblocks)
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (q >= 4) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; b++) s += part[(long long)b * 4 + q];
-  out[q] = s;
+  double v = 0.0;
+  for (int b = lane; b < nblocks; b += 32) v += part[(long long)b * 4 + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) out[q] = v;
 }
 
-__global__ void kron_scale_kernel(const double* __restrict__ in, const double* __restrict__ lam, KronSizes s, int skip,
-                                  int power_inv_A, const double* __restrict__ noise_inv, double add, long long total,
-                                  double* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    double v = (in ? in[i] : 1.0) * kron_lambda_prod(i, s, lam, skip);
-    if (power_inv_A) v /= (kron_lambda_prod(i, s, lam, -1) + (noise_inv ? noise_inv[0] : 0.0) + add);
-    out[i] = v;
+template <bool PAIRS>
+__global__ void __launch_bounds__(256) kron_scale_kernel(const double* __restrict__ in, const double* __restrict__ lam,
+                                                         KronSizes s, int skip, int power_inv_A,
+                                                         const double* __restrict__ noise_inv, double add, long long total,
+                                                         double* __restrict__ out) {
+  const double tau = (noise_inv ? noise_inv[0] : 0.0) + add;
+  if (PAIRS) {
+    const int last = s.nmodes - 1;
+    const unsigned npairs = (unsigned)(total >> 1);
+    for (unsigned pi = blockIdx.x * 256u + threadIdx.x; pi < npairs; pi += gridDim.x * 256u) {
+      unsigned il;
+      const double pre_all = kron_prefix_prod(2u * pi, s, lam, -1, il);
+      const double l0 = lam[s.off[last] + il], l1 = lam[s.off[last] + il + 1];
+      double pre = pre_all;
+      if (skip >= 0 && skip < last) { unsigned dummy; pre = kron_prefix_prod(2u * pi, s, lam, skip, dummy); }
+      double2 v = in ? reinterpret_cast<const double2*>(in)[pi] : make_double2(1.0, 1.0);
+      v.x *= (skip == last) ? pre : pre * l0;
+      v.y *= (skip == last) ? pre : pre * l1;
+      if (power_inv_A) { v.x /= fma(pre_all, l0, tau); v.y /= fma(pre_all, l1, tau); }
+      reinterpret_cast<double2*>(out)[pi] = v;
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+      double v = (in ? in[i] : 1.0) * kron_lambda_prod(i, s, lam, skip);
+      if (power_inv_A) v /= (kron_lambda_prod(i, s, lam, -1) + tau);
+      out[i] = v;
+    }
   }
 }
 
@@ -362,6 +741,192 @@ __global__ void __launch_bounds__(SYEVJ_THREADS) syevj_kernel(const double* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Jacobi eigensolver for n <= 128 (every per-mode matrix of the reference's configs): a CLUSTER OF TWO CTAs per
+// matrix.  A single CTA is bound by shared-memory / L2 bandwidth (profiles/r01_kron_bench_v2.txt: 8 us per
+// round-robin step at n = 128 with A in shared memory and V^T in L2; the first version, with serialised L2 round
+// trips, 13 us).  Here CTA 0 keeps A in its shared memory and CTA 1 keeps V^T in its own; per step
+//   CTA 0: the m/2 rotations of the step -> written to BOTH CTAs' rotation buffers (DSMEM stores), cluster barrier,
+//          then ONE fused pass over A: every 2x2 block (pair k1 x pair k2) is read once, rotated from the left and
+//          the right, and written once (half the shared-memory traffic of a row pass + a column pass);
+//   CTA 1: cluster barrier, then the row rotations of V^T - concurrently with CTA 0's pass over A.
+// Pairs follow the round-robin tournament in (a, b) order (not sorted), so consecutive pair slots touch consecutive
+// rows/columns: conflict-free shared-memory access.  Rotation buffers are double-buffered by step parity; the one
+// cluster barrier per step is the only cross-CTA synchronisation.
+// ---------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 512;
+
+__device__ __forceinline__ void rr_pair_ab(int step, int k, int m, int& a, int& b) {
+  const int mm = m - 1;
+  if (k == 0) { a = step % mm; b = mm; }
+  else { a = (step + k) % mm; b = (step - k + mm) % mm; }
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_st_f64(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_s32(uint32_t addr, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SC_THREADS, 1)
+syevj_cluster_kernel(const double* __restrict__ Ain, int n, double* __restrict__ w, double* __restrict__ V,
+                     int* __restrict__ info, int max_sweeps) {
+  extern __shared__ __align__(16) double sm[];
+  const int b = blockIdx.x >> 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_rank();
+  const int m = (n + 1) & ~1, half = m / 2, lda = m + 1;
+  double* mat = sm;                                   // rank 0: A [m][lda];  rank 1: V^T [m][lda] (rows = eigenvectors)
+  double* rc = mat + (size_t)m * lda;                 // [2][half] cos, by step parity
+  double* rs = rc + 2 * half;                         // [2][half] sin
+  int* ra = reinterpret_cast<int*>(rs + 2 * half);    // [2][half] first index of the pair
+  int* rb = ra + 2 * half;                            // [2][half] second index
+  int* perm = rb + 2 * half;                          // [m] rank of eigenvalue i (ascending)
+  int* flag = perm + m;                               // [2]: converged, pad
+  double* red = reinterpret_cast<double*>(flag + 2);  // [SC_THREADS / 32]
+  const double* A0 = Ain + (long long)b * n * n;
+
+  double nrm_local = 0.0;
+  for (int e = tid; e < m * m; e += SC_THREADS) {
+    const int i = e / m, j = e - i * m;
+    double v = 0.0;
+    if (rank == 0) {
+      // symmetrise from the UPPER triangle (torch.linalg.eigh(K, UPLO='U'), reference hogp.py:20)
+      if (i < n && j < n) v = (j >= i) ? A0[(long long)i * n + j] : A0[(long long)j * n + i];
+      nrm_local = fma(v, v, nrm_local);
+    } else {
+      v = (i == j) ? 1.0 : 0.0;
+    }
+    mat[i * lda + j] = v;
+  }
+  if (tid == 0) flag[0] = 0;
+  auto block_sum = [&](double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < SC_THREADS / 32; k++) t += red[k];
+    return t;
+  };
+  const double norm2 = block_sum(nrm_local);          // meaningful in rank 0 only
+  const uint32_t r_rc = dsmem_addr(rc, 1), r_rs = dsmem_addr(rs, 1), r_ra = dsmem_addr(ra, 1), r_rb = dsmem_addr(rb, 1);
+  const uint32_t r_flag = dsmem_addr(flag, 1), r_perm = dsmem_addr(perm, 1);
+  cluster_sync_all();                                  // both CTAs resident and initialised before any DSMEM store
+
+  int converged = 0;
+  if (rank == 0 && norm2 == 0.0) converged = 1;
+  // a zero matrix converges immediately; publish that like any sweep result so that both CTAs agree
+  if (rank == 0 && tid == 0 && converged) { flag[0] = 1; dsmem_st_s32(r_flag, 1); }
+  cluster_sync_all();
+  converged = flag[0];
+  for (int sweep = 0; sweep < max_sweeps && !converged; sweep++) {
+    double off_local = 0.0;
+    for (int step = 0; step < m - 1; step++) {
+      const int bo = (step & 1) * half;
+      if (rank == 0 && tid < half) {
+        int ia, ib; rr_pair_ab(step, tid, m, ia, ib);
+        double c = 1.0, s = 0.0;
+        if (ia < n && ib < n) {
+          const double apq = mat[ia * lda + ib], app = mat[ia * lda + ia], aqq = mat[ib * lda + ib];
+          off_local = fma(apq, apq, off_local);
+          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-19 * (fabs(app) + fabs(aqq))) {
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double tt = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = rsqrt(1.0 + tt * tt);
+            s = tt * c;
+          }
+        }
+        const int o = bo + tid;
+        rc[o] = c; rs[o] = s; ra[o] = ia; rb[o] = ib;
+        dsmem_st_f64(r_rc + o * 8, c); dsmem_st_f64(r_rs + o * 8, s);
+        dsmem_st_s32(r_ra + o * 4, ia); dsmem_st_s32(r_rb + o * 4, ib);
+      }
+      cluster_sync_all();
+      if (rank == 0) {
+        // fused two-sided update: block (k1, k2) = rows (a1, b1) x columns (a2, b2):  X' = G1 X G2^T, G = [[c, -s], [s, c]]
+        for (int e = tid; e < half * half; e += SC_THREADS) {
+          const int k1 = e / half, k2 = e - k1 * half;
+          const double s1 = rs[bo + k1], s2 = rs[bo + k2];
+          if (s1 != 0.0 || s2 != 0.0) {
+            const double c1 = rc[bo + k1], c2 = rc[bo + k2];
+            double* r0 = mat + ra[bo + k1] * lda;
+            double* r1 = mat + rb[bo + k1] * lda;
+            const int ca = ra[bo + k2], cb = rb[bo + k2];
+            const double x00 = r0[ca], x01 = r0[cb], x10 = r1[ca], x11 = r1[cb];
+            const double y00 = c1 * x00 - s1 * x10, y01 = c1 * x01 - s1 * x11;
+            const double y10 = s1 * x00 + c1 * x10, y11 = s1 * x01 + c1 * x11;
+            r0[ca] = c2 * y00 - s2 * y01; r0[cb] = s2 * y00 + c2 * y01;
+            r1[ca] = c2 * y10 - s2 * y11; r1[cb] = s2 * y10 + c2 * y11;
+          }
+        }
+        __syncthreads();
+      } else {
+        for (int e = tid; e < half * n; e += SC_THREADS) {
+          const int k = e / n, j = e - k * n;
+          const double s = rs[bo + k];
+          if (s != 0.0) {
+            const double c = rc[bo + k];
+            double* vp_ = mat + ra[bo + k] * lda + j;
+            double* vq_ = mat + rb[bo + k] * lda + j;
+            const double vp = *vp_, vq = *vq_;
+            *vp_ = c * vp - s * vq;
+            *vq_ = s * vp + c * vq;
+          }
+        }
+      }
+    }
+    if (rank == 0) {
+      const double off2 = block_sum(off_local);
+      if (tid == 0) {
+        const int cv = (off2 <= 1e-26 * norm2) ? 1 : 0;
+        flag[0] = cv;
+        dsmem_st_s32(r_flag, cv);
+      }
+    }
+    cluster_sync_all();
+    converged = flag[0];
+  }
+  if (rank == 0) {
+    if (tid == 0 && !converged) info[b] = 1;
+    // ascending order by rank, ties broken by index
+    for (int i = tid; i < n; i += SC_THREADS) {
+      const double li = mat[i * lda + i];
+      int rk = 0;
+      for (int j = 0; j < n; j++) {
+        const double lj = mat[j * lda + j];
+        rk += (lj < li) || (lj == li && j < i);
+      }
+      w[(long long)b * n + rk] = li;
+      dsmem_st_s32(r_perm + i * 4, rk);
+    }
+  }
+  cluster_sync_all();
+  if (rank == 1) {
+    for (int e = tid; e < n * n; e += SC_THREADS) {
+      const int r = e / n, i = e - r * n;        // V[r][rank(i)] = V^T[i][r]
+      V[(long long)b * n * n + (long long)r * n + perm[i]] = mat[i * lda + r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // d(sum gK o K)/d(inv_ls, amp), K rectangular [n1][n2]; partial per 64x64 tile, then grad_finish (dense_kernels.cuh)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kernel_bwd_kernel(const double* __restrict__ x1, const double* __restrict__ x2,
@@ -437,6 +1002,11 @@ __global__ void kernel_bwd_finish_kernel(const double* __restrict__ partial, int
   }
 }
 
+static bool kron_pairs_ok(const int* sizes, int nmodes, long long total, const void* a, const void* b, const void* c) {
+  return nmodes >= 1 && nmodes <= 8 && !(sizes[nmodes - 1] & 1) && total < (1LL << 31) &&
+         !(((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15);
+}
+
 static KronSizes make_sizes(const int* sizes, int nmodes) {
   KronSizes s;
   memset(&s, 0, sizeof(s));
@@ -452,20 +1022,79 @@ using namespace ffgp;
 
 extern "C" {
 
+static int ms_num_sms() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+  }
+  return v;
+}
+
 int ffgp_mode_dot_f64(const double* t, const double* mat, double* out, long long outer, int I, long long inner, int J,
                       int transpose_mat, void* stream) {
   if (!t || !mat || !out) return fail(-1, "ffgp_mode_dot_f64: null pointer%s", "");
   if (outer <= 0 || I <= 0 || inner <= 0 || J <= 0) return fail(-2, "ffgp_mode_dot_f64: bad size%s", "");
   const long long ncols = outer * inner;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool aligned16 = !(((uintptr_t)t | (uintptr_t)out) & 15);
+  // (1) small factor matrix: streaming kernel, factor resident in shared memory
+  if (I <= 128 && J <= 128 && aligned16 && ((inner == 1 && !(I & 1)) || (inner > 1 && !(inner & 1)))) {
+    ModeSmallParams p;
+    p.t = t; p.mat = mat; p.out = out; p.ncols = ncols; p.inner = inner; p.I = I; p.J = J; p.transpose_mat = transpose_mat;
+    p.Ip = (I + 3) & ~3; p.Jp = (J + 7) & ~7;
+    p.SA = p.Ip + ((4 - p.Ip % 16) + 16) % 16;             // smallest stride >= Ip with SA = 4 (mod 16)
+    const size_t smem = ((size_t)std::min(p.Jp, 64) * p.SA + (size_t)MS_WARPS * MS_STAGES * MS_STAGE_DOUBLES) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+      FFGP_CUDA(cudaFuncSetAttribute(mode_dot_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      FFGP_CUDA(cudaFuncSetAttribute(mode_dot_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      attr = true;
+    }
+    const long long nchunks = (ncols + 63) / 64;                // 8 warps x 8-column blocks per CTA pass
+    const int per_sm = std::max(1, std::min(2, (int)((220 * 1024) / smem)));
+    const int gx = (int)std::min<long long>(nchunks, std::max(1, ms_num_sms() * per_sm / ((p.Jp + 63) / 64)));
+    const dim3 grid(gx, (p.Jp + 63) / 64);
+    if (inner == 1) mode_dot_small_kernel<true><<<grid, 256, smem, st>>>(p);
+    else mode_dot_small_kernel<false><<<grid, 256, smem, st>>>(p);
+    ++ffgp::g_launches;
+    FFGP_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // (2) large factor matrix (e.g. Tensor_linear 1024 -> 4096, gp_computation_pack.py:155-158): this IS a GEMM - the
+  //     tiled DMMA GEMM of the dense path, batched over `outer`
+  if ((I > 128 || J > 128) && I % 16 == 0 && J % 64 == 0) {
+    if (inner == 1 && ncols % 64 == 0)          // out[c][j] = sum_k t[c][k] mat(j,k)
+      return ffgp_gemm_f64(1, transpose_mat ? 0 : 1, t, I, 0, mat, transpose_mat ? J : I, 0, out, J, 0, (int)ncols, J, I, 1.0,
+                           0.0, 0, 0, 1, stream);
+    if (inner > 1 && inner % 64 == 0 && outer < (1 << 16))   // out_o[j][c] = sum_k mat(j,k) t_o[k][c]
+      return ffgp_gemm_f64(transpose_mat ? 0 : 1, 0, mat, transpose_mat ? J : I, 0, t, (int)inner, (long long)I * inner, out,
+                           (int)inner, (long long)J * inner, J, (int)inner, I, 1.0, 0.0, 0, 0, (int)outer, stream);
+  }
+  // (3) anything else: generic kernel
   const long long nchunks = (ncols + MD_COLS - 1) / MD_COLS;
   const int gx = (int)std::min<long long>(nchunks, 148LL * 8);
-  mode_dot_kernel<<<dim3(gx, (J + 127) / 128), 256, 0, (cudaStream_t)stream>>>(t, mat, out, ncols, I, inner, J, transpose_mat);
+  mode_dot_kernel<<<dim3(gx, (J + 127) / 128), 256, 0, st>>>(t, mat, out, ncols, I, inner, J, transpose_mat);
   ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int gram_slices(long long ncols, int Ja, int Jb) {
+static bool gram_stream_ok(const void* X, const void* Y, long long inner, int Ja, int Jb) {
+  if (((uintptr_t)X | (uintptr_t)Y) & 15) return false;
+  return inner == 1 ? (!(Ja & 1) && !(Jb & 1)) : !(inner & 1);
+}
+
+static int gram_slices(long long ncols, int Ja, int Jb, bool stream) {
+  if (stream) {
+    const int tile = (Ja <= 32 && Jb <= 32) ? 32 : 64;
+    const long long tiles = (long long)((Ja + tile - 1) / tile) * ((Jb + tile - 1) / tile);
+    const long long nchunks = (ncols + GS_CH - 1) / GS_CH;
+    const long long want = std::max<long long>(1, ((long long)ms_num_sms() * (tile == 32 ? 2 : 1)) / tiles);
+    return (int)std::max<long long>(1, std::min(want, nchunks));
+  }
   const long long tiles = (long long)((Ja + MG_T - 1) / MG_T) * ((Jb + MG_T - 1) / MG_T);
   long long want = std::max<long long>(1, (148LL * 4) / tiles);
   long long maxs = std::max<long long>(1, ncols / 256);
@@ -473,7 +1102,9 @@ static int gram_slices(long long ncols, int Ja, int Jb) {
 }
 
 size_t ffgp_mode_gram_scratch_bytes(long long outer, long long inner, int Ja, int Jb) {
-  return (size_t)gram_slices(outer * inner, Ja, Jb) * Ja * Jb * sizeof(double) + 256;
+  // upper bound over both kernels (the streaming path is chosen by pointer alignment at call time)
+  const int ns = std::max(gram_slices(outer * inner, Ja, Jb, true), gram_slices(outer * inner, Ja, Jb, false));
+  return (size_t)ns * Ja * Jb * sizeof(double) + 256;
 }
 
 int ffgp_mode_gram_f64(const double* X, const double* Y, double* G, long long outer, long long inner, int Ja, int Jb,
@@ -482,14 +1113,25 @@ int ffgp_mode_gram_f64(const double* X, const double* Y, double* G, long long ou
   if (outer <= 0 || inner <= 0 || Ja <= 0 || Jb <= 0) return fail(-2, "ffgp_mode_gram_f64: bad size%s", "");
   if (scratch_bytes < ffgp_mode_gram_scratch_bytes(outer, inner, Ja, Jb)) return fail(-3, "ffgp_mode_gram_f64: scratch too small%s", "");
   const long long ncols = outer * inner;
-  const int ns = gram_slices(ncols, Ja, Jb);
-  long long cps = (ncols + ns - 1) / ns;
-  cps = (cps + MG_KC - 1) / MG_KC * MG_KC;
   cudaStream_t st = (cudaStream_t)stream;
-  mode_gram_kernel<<<dim3((Jb + MG_T - 1) / MG_T, (Ja + MG_T - 1) / MG_T, ns), 256, 0, st>>>(X, Y, (double*)scratch, ncols, inner,
-                                                                                             Ja, Jb, cps);
+  const bool stream_path = gram_stream_ok(X, Y, inner, Ja, Jb);
+  const int ns = gram_slices(ncols, Ja, Jb, stream_path);
+  if (stream_path) {
+    const bool small = Ja <= 32 && Jb <= 32;
+    cudaError_t e;
+    if (inner == 1) e = small ? launch_gram_stream<32, true>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st)
+                              : launch_gram_stream<64, true>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st);
+    else e = small ? launch_gram_stream<32, false>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st)
+                   : launch_gram_stream<64, false>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st);
+    FFGP_CUDA(e);
+  } else {
+    long long cps = (ncols + ns - 1) / ns;
+    cps = (cps + MG_KC - 1) / MG_KC * MG_KC;
+    mode_gram_kernel<<<dim3((Jb + MG_T - 1) / MG_T, (Ja + MG_T - 1) / MG_T, ns), 256, 0, st>>>(X, Y, (double*)scratch, ncols, inner,
+                                                                                               Ja, Jb, cps);
+    FFGP_CUDA(cudaGetLastError());
+  }
   ++ffgp::g_launches;
-  FFGP_CUDA(cudaGetLastError());
   const long long nelem = (long long)Ja * Jb;
   gram_reduce_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>((const double*)scratch, ns, nelem, G);
   ++ffgp::g_launches;
@@ -513,10 +1155,13 @@ int ffgp_kron_core_f64(const double* T1, const double* lambdas, const int* sizes
   for (int m = 0; m < nmodes; m++) total *= sizes_host[m];
   const int nb = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  kron_core_kernel<<<nb, 256, 0, st>>>(T1, lambdas, s, noise_inv, add_scalar, total, out_core, out_A, (double*)scratch);
+  if (kron_pairs_ok(sizes_host, nmodes, total, T1, out_core, out_A))
+    kron_core_kernel<true><<<nb, 256, 0, st>>>(T1, lambdas, s, noise_inv, add_scalar, total, out_core, out_A, (double*)scratch);
+  else
+    kron_core_kernel<false><<<nb, 256, 0, st>>>(T1, lambdas, s, noise_inv, add_scalar, total, out_core, out_A, (double*)scratch);
   ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
-  kron_sums_finish_kernel<<<1, 32, 0, st>>>((const double*)scratch, nb, out_sums);
+  kron_sums_finish_kernel<<<1, 128, 0, st>>>((const double*)scratch, nb, out_sums);
   ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
@@ -530,7 +1175,10 @@ int ffgp_kron_scale_f64(const double* in, const double* lambdas, const int* size
   long long total = 1;
   for (int m = 0; m < nmodes; m++) total *= sizes_host[m];
   const int nb = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
-  kron_scale_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(in, lambdas, s, skip_mode, divide_by_A, noise_inv, add_scalar, total, out);
+  if (kron_pairs_ok(sizes_host, nmodes, total, in, out, nullptr))
+    kron_scale_kernel<true><<<nb, 256, 0, (cudaStream_t)stream>>>(in, lambdas, s, skip_mode, divide_by_A, noise_inv, add_scalar, total, out);
+  else
+    kron_scale_kernel<false><<<nb, 256, 0, (cudaStream_t)stream>>>(in, lambdas, s, skip_mode, divide_by_A, noise_inv, add_scalar, total, out);
   ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
@@ -548,18 +1196,24 @@ int ffgp_syevj_f64(const double* A, int n, int batch, double* w, double* V, void
   if (workspace_bytes < ffgp_syevj_workspace_bytes(n, batch)) return fail(-3, "ffgp_syevj_f64: workspace too small%s", "");
   cudaStream_t st = (cudaStream_t)stream;
   const int m = (n + 1) & ~1;
-  const bool in_smem = n <= SYEVJ_SMEM_N;
-  size_t smem = (size_t)(m + SYEVJ_THREADS) * sizeof(double);
-  if (in_smem) smem += (size_t)n * (n + 1) * sizeof(double);
   static bool attr = false;
   if (!attr) {
     FFGP_CUDA(cudaFuncSetAttribute(syevj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FFGP_CUDA(cudaFuncSetAttribute(syevj_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   double* vt = (double*)workspace;
-  double* wa = in_smem ? nullptr : vt + (size_t)batch * n * n;
   FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
-  syevj_kernel<<<batch, SYEVJ_THREADS, smem, st>>>(A, n, w, V, wa, vt, info, 40);
+  if (n <= SYEVJ_SMEM_N) {
+    const int half = m / 2;
+    const size_t smem = ((size_t)m * (m + 1) + 4 * half) * sizeof(double) + (size_t)(4 * half + m + 2) * sizeof(int) +
+                        (SC_THREADS / 32) * sizeof(double) + 16;
+    syevj_cluster_kernel<<<2 * batch, SC_THREADS, smem, st>>>(A, n, w, V, info, 40);
+  } else {
+    const size_t smem = (size_t)(m + SYEVJ_THREADS) * sizeof(double);
+    double* wa = vt + (size_t)batch * n * n;
+    syevj_kernel<<<batch, SYEVJ_THREADS, smem, st>>>(A, n, w, V, wa, vt, info, 40);
+  }
   ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;

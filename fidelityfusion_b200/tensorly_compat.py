@@ -107,23 +107,34 @@ def ones(shape, **kw):
 # ---------------------------------------------------------------------------------------------
 # Kronecker GP core: per-mode eigh -> T1 -> (A, core, sums) -> g, with the analytic gradient
 # ---------------------------------------------------------------------------------------------
-def eigh(K):
-    """Ascending eigenpairs of a symmetric matrix (upper triangle read), Jacobi in shared memory.
-    No autograd: the Kronecker loss below differentiates analytically w.r.t. K instead of through eigh."""
+def _eigh_launch(K):
+    """Enqueue the Jacobi eigensolver; returns (w, V, info) without synchronising."""
     L = B.lib()
     Kc = ops._f64c(K).unsqueeze(0)
     n = Kc.shape[-1]
     dev = K.device
     w = torch.empty(1, n, dtype=torch.float64, device=dev)
     V = torch.empty(1, n, n, dtype=torch.float64, device=dev)
-    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    info = torch.empty(1, dtype=torch.int32, device=dev)
     wsb = L.ffgp_syevj_workspace_bytes(n, 1)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ws = ops._ws_cache.get(wsb, dev)
     rc = L.ffgp_syevj_f64(B.ptr(Kc), n, 1, B.ptr(w), B.ptr(V), B.ptr(ws), wsb, B.ptr(info), B.stream_ptr())
     B.check(rc, 'ffgp_syevj_f64')
-    if int(info[0]) != 0:
+    return w[0], V[0], info
+
+
+def _eigh_check(infos):
+    """One device->host read for all the eigensolves of a call (torch.linalg.eigh raises on failure; so do we)."""
+    if int(torch.cat(infos).abs().sum()) != 0:
         raise torch.linalg.LinAlgError('ffgp.eigh: Jacobi sweeps did not converge')
-    return w[0].to(K.dtype), V[0].to(K.dtype)
+
+
+def eigh(K):
+    """Ascending eigenpairs of a symmetric matrix (upper triangle read), Jacobi in shared memory.
+    No autograd: the Kronecker loss below differentiates analytically w.r.t. K instead of through eigh."""
+    w, V, info = _eigh_launch(K)
+    _eigh_check([info])
+    return w.to(K.dtype), V.to(K.dtype)
 
 
 def _sizes_arr(sizes):
@@ -165,7 +176,9 @@ class _KronNLL(torch.autograd.Function):
         dev = Y.device
         Yc = ops._f64c(Y)
         sizes = list(Yc.shape)
-        eig = [eigh(ops._f64c(K)) for K in Ks]
+        launched = [_eigh_launch(K) for K in Ks]          # all modes enqueued back to back, one status read
+        _eigh_check([l[2] for l in launched])
+        eig = [(l[0], l[1]) for l in launched]
         lam_cat = torch.cat([e[0] for e in eig]).contiguous()
         T1 = Yc
         for k, (_, U) in enumerate(eig):

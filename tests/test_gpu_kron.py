@@ -29,7 +29,11 @@ def _f64_default():
 
 @pytest.mark.parametrize('shape,mode,J', [((5, 4, 6), 1, 8), ((5, 4, 6), 2, 12), ((5, 4, 6), 0, 3), ((16, 8, 8, 4), 2, 8),
                                           ((16, 8, 8, 4), 3, 4), ((128, 32, 32, 16), 0, 128), ((128, 32, 32, 16), 1, 32),
-                                          ((128, 32, 32, 16), 3, 16), ((48, 16), 1, 64), ((3, 130, 7), 1, 140), ((1, 1, 1), 1, 1)])
+                                          ((128, 32, 32, 16), 3, 16), ((48, 16), 1, 64), ((3, 130, 7), 1, 140), ((1, 1, 1), 1, 1),
+                                          # streaming small-factor kernel: ragged I/J, several k-blocks, odd J on the last mode
+                                          ((7, 10, 6), 1, 9), ((9, 6), 1, 7), ((2, 70, 6), 1, 70), ((3, 100, 2), 1, 128), ((200, 34), 1, 99),
+                                          # large factor matrices go through the tiled DMMA GEMM (Tensor_linear 1024 -> 4096 shape class)
+                                          ((128, 256), 1, 192), ((4, 144, 64), 1, 192), ((64, 1024), 1, 1024)])
 def test_mode_dot_and_its_gradients(shape, mode, J):
     from fidelityfusion_b200 import tensorly_compat as tl
     gen = torch.Generator().manual_seed(sum(shape) + mode)
