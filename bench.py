@@ -27,6 +27,9 @@ N_C2, D_C2 = 8192, 16
 F_ALG_C2 = N_C2 ** 3 + 4 * N_C2 ** 2 * D_C2 + 4 * N_C2 ** 2 * 1            # 5.543e11 FLOP / eval
 B_C5, N_C5, D_C5, NS_C5 = 4096, 512, 8, 64
 F_ALG_C5 = N_C5 ** 3 + 4 * N_C5 ** 2 * D_C5 + 4 * N_C5 ** 2 * 1            # 1.437e8 FLOP / GP
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE S = M^T M launch of the dominant kernel at N=8192 (ncu,
+# profiles/r01_metrics_c2_v1.txt: 2 launches read 2794 MB and wrote 460 MB); algorithmic bytes 8 N^2 = 537 MB
+TRAFFIC_LAUUM_BYTES = 1.627e9
 
 
 def c2_inputs(torch):
@@ -61,23 +64,39 @@ class ClockSampler:
         self._t = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(',')])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        # ONE long-lived nvidia-smi in loop mode (-lms 100): a fresh process per sample costs ~250 ms and a 0.5 s timed
+        # region would see two samples
+        try:
+            self._proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                           str(self.index), '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          text=True)
+        except Exception:
+            return
+        for line in self._proc.stdout:
+            if self._stop.is_set():
+                break
+            line = line.strip()
+            if line and self._armed.is_set():
+                self.samples.append([f.strip() for f in line.split(',')])
+
+    def arm(self):
+        """Start recording (call right before the timed region; the process is already warm)."""
+        self._armed.set()
 
     def __enter__(self):
+        self._armed = threading.Event()
+        self._proc = None
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
+        if self._proc is not None:
+            try:
+                self._proc.terminate()
+            except Exception:
+                pass
         self._t.join(timeout=10)
 
     def summary(self):
@@ -217,18 +236,20 @@ def main():
         loss.backward()
         return loss
 
+    clk = ClockSampler(local)
+    clk.__enter__()                                      # nvidia-smi loop process starts now, recording is armed below
     for _ in range(args.warmup):
         one_eval(xd, yd)
     barrier()
     launches0 = lib.ffgp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            loss = one_eval(xd, yd)
-        e1.record()
-        barrier()
+    clk.arm()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_eval(xd, yd)
+    e1.record()
+    barrier()
     launches = int(lib.ffgp_launch_count() - launches0)
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     nll_val = float(loss.item())
@@ -252,6 +273,31 @@ def main():
     ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps)
     e2e = {'value': world * 1e3 / ms_e2e, 'unit': 'evals/s', 'h2d_bytes_per_step': int(xh.numel() * 8 + yh.numel() * 8),
            'd2h_bytes_per_step': int(res.numel() * 8), 'ms_per_step': ms_e2e}
+    clk.__exit__()                                       # clocks sampled over the device-timed and the e2e loops
+
+    # ------------------------------------------------------------------ dominant kernel alone: the TMA + DMMA GEMM in its
+    # S = M^T M launch shape (lower tiles, K range [i0, N)): N^3/3 algorithmic FLOP per launch, CUDA events
+    kern = None
+    if rank == 0:
+        n = N_C2
+        Mt = torch.tril(torch.randn(n, n, device='cuda'))
+        St = torch.empty(n, n, device='cuda')
+        def lauum():
+            rc = lib.ffgp_gemm_f64(0, 0, _lib.ptr(Mt), n, 0, _lib.ptr(Mt), n, 0, _lib.ptr(St), n, 0, n, n, n, 1.0, 0.0, 1, 4, 1,
+                                   _lib.stream_ptr())
+            assert rc == 0
+        for _ in range(3):
+            lauum()
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(10):
+            lauum()
+        k1.record(); torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / 10
+        kern = {'name': 'gemm_tma_kernel<0,0> (S = M^T M launch of the gradient, 2080 lower 128x128 tiles)',
+                'flop_per_launch': n ** 3 / 3, 'ms_per_launch': kms, 'achieved': n ** 3 / 3 / kms * 1e-9}
+        del Mt, St
 
     # ------------------------------------------------------------------ batched C5, sharded across ranks
     batched = None
@@ -305,9 +351,11 @@ def main():
         'e2e': e2e,
         'gpu_launches': launches,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': None,
+                     'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': TRAFFIC_LAUUM_BYTES,
+                     'kernel': kern,
                      'note': 'FP64 tensor pipe (DMMA). achieved = F_alg (N^3 + 4N^2 d + 4N^2 D = 5.543e11 FLOP/eval, SURVEY 8d) / '
                              'CUDA-event time of the whole eval (all launches; the DMMA GEMM kernel is >90% of it). '
+                             "'kernel' = the dominant kernel timed alone (its own achieved TFLOP/s on N^3/3 FLOP); 'traffic' = its DRAM bytes per launch from ncu. "
                              'peak = torch.matmul fp64 8192^3 best of 10 measured live in this run (MEASURED_PEAKS.json has '
                              'no fp64 entry); DMMA issue-bound peak measured at 37.1 TFLOP/s (profiles/r01_fp64_peak_microbench.txt)'},
         'clocks': clk.summary(),

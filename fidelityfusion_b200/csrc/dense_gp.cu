@@ -54,10 +54,44 @@ static bool use_tma_gemm() {
   return v != 0;
 }
 
+static thread_local int g_cta_cap = 0;   // > 0: see gemm()
+
 static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long long sA, const double* B, int ldb,
                         long long sB, double* C, int ldc, long long sC, int M, int N, int K, double alpha, double beta,
                         int lower_only, int kmode, int batch, cudaStream_t st, int inner = 1, long long iA = 0,
                         long long iB = 0, long long iC = 0) {
+  // Background launches (g_cta_cap > 0) are cut into bands of at most g_cta_cap CTAs: a grid that fills every SM with
+  // long-K tiles would make the high-priority panel chain wait for a tile to retire at every one of its launches
+  // (a 128x128 TMA GEMM CTA owns its SM's whole register file).  Bands run back to back on the same stream.
+  if (g_cta_cap > 0 && !lower_only && batch == 1 && M % 128 == 0 && N % 128 == 0) {
+    const int cap = g_cta_cap;
+    const int tm = M / 128, tn = N / 128;
+    if ((long long)tm * tn * inner > cap) {
+      g_cta_cap = 0;
+      cudaError_t e = cudaSuccess;
+      if (inner > 1) {
+        const int per = std::max(1, cap / (tm * tn));
+        for (int n0 = 0; n0 < inner && e == cudaSuccess; n0 += per) {
+          g_cta_cap = (tm * tn > cap) ? cap : 0;       // a single node larger than the cap is banded by the recursion
+          e = gemm(a_kmaj, b_kmaj, A + n0 * iA, lda, sA, B + n0 * iB, ldb, sB, C + n0 * iC, ldc, sC, M, N, K, alpha, beta,
+                   lower_only, kmode, 1, st, std::min(per, inner - n0), iA, iB, iC);
+          g_cta_cap = 0;
+        }
+      } else if (kmode == K_LE_ROW || kmode == K_GE_ROW) {   // K range depends on the tile ROW: band along N
+        const int per = std::max(1, cap / tm) * 128;
+        for (int c0 = 0; c0 < N && e == cudaSuccess; c0 += per)
+          e = gemm(a_kmaj, b_kmaj, A, lda, sA, b_kmaj ? B + (long long)c0 * ldb : B + c0, ldb, sB, C + c0, ldc, sC, M,
+                   std::min(per, N - c0), K, alpha, beta, 0, kmode, 1, st);
+      } else {                                               // K range depends on the tile COLUMN (or not at all): band along M
+        const int per = std::max(1, cap / tn) * 128;
+        for (int r0 = 0; r0 < M && e == cudaSuccess; r0 += per)
+          e = gemm(a_kmaj, b_kmaj, a_kmaj ? A + (long long)r0 * lda : A + r0, lda, sA, B, ldb, sB, C + (long long)r0 * ldc, ldc,
+                   sC, std::min(per, M - r0), N, K, alpha, beta, 0, kmode, 1, st);
+      }
+      g_cta_cap = cap;
+      return e;
+    }
+  }
   GemmParams p;
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = sA; p.sB = sB; p.sC = sC; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only; p.kmode = kmode;
@@ -364,6 +398,12 @@ static cudaError_t trtri_bottom_up_range(const FactorCtx& c, int off, int n) {
 //   M21 = -M22 L21 M11  =  -M22 (L21 M11)
 // has half of its FLOPs (inverse of the leading half, then W = L21 M11) depending only on the LEADING half of L,
 // which is final at the midpoint.  Streams: panel chain (highest priority) > trailing updates > background W.
+static int bg_cta_cap() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_BG_CAP"); v = e ? atoi(e) : (num_sms() * 2) / 3; }
+  return v;
+}
+
 static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int stop_after, bool* done) {
   *done = false;
   int NB = outer_nb();
@@ -388,10 +428,14 @@ static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int 
     cudaError_t e2;
     if ((e2 = cudaEventRecord(aux->ev_half, cb.st)) != cudaSuccess) return e2;
     if ((e2 = cudaStreamWaitEvent(cg.st, aux->ev_half, 0)) != cudaSuccess) return e2;
-    if ((e2 = trtri_bottom_up_range(cg, 0, h)) != cudaSuccess) return e2;
+    g_cta_cap = bg_cta_cap();
+    e2 = trtri_bottom_up_range(cg, 0, h);
     // W = L21 M11 -> A21 (dead: every block column of the leading half has been solved)
-    return gemm(true, false, c.L + o21, c.ld, c.sb, c.M, c.ld, c.sb, c.A + o21, c.ld, c.sb, h, h, h, 1.0, 0.0, 0, K_GE_COL,
+    if (e2 == cudaSuccess)
+      e2 = gemm(true, false, c.L + o21, c.ld, c.sb, c.M, c.ld, c.sb, c.A + o21, c.ld, c.sb, h, h, h, 1.0, 0.0, 0, K_GE_COL,
                 c.batch, cg.st);
+    g_cta_cap = 0;
+    return e2;
   };
   if ((e = potrf_right_looking(cb, np, true, at_half)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(aux->ev_join, cb.st)) != cudaSuccess) return e;

@@ -125,9 +125,7 @@ __global__ void __launch_bounds__(256) mode_dot_kernel(const double* __restrict_
 // Algorithmic bytes: 8 (I + J) per generalised column + the factor.
 // ---------------------------------------------------------------------------------------------
 constexpr int MS_KB = 32, MS_STAGES = 4;
-constexpr int MS_LD_COLS = 12;            // LAST == false: [MS_KB][8 cols + 4]   (12 t + g distinct mod 16)
-constexpr int MS_LD_K = MS_KB + 4;        // LAST == true:  [8 rows][36]
-constexpr int MS_STAGE_DOUBLES = MS_KB * MS_LD_COLS;     // 384 >= 8 * 36
+constexpr int MS_STAGE_DOUBLES = 256;     // 32 k x 8 columns, or 8 rows x 32 k: 2 KB, XOR-swizzled instead of padded
 constexpr int MS_WARPS = 8;
 
 struct ModeSmallParams {
@@ -142,17 +140,22 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return v;
 }
 
-template <bool LAST>
-__global__ void __launch_bounds__(256, 2) mode_dot_small_kernel(const ModeSmallParams p) {
+// Shared-memory tile layouts (doubles), both conflict-free for the m8n8k4 fragment loads without padding:
+//   LAST == false: element (k, col) at k * 8 + (col ^ (4 * ((k >> 1) & 1)))
+//   LAST == true : element (row, k) at row * 32 + (k ^ (4 * (row & 3)))
+// MT = number of 8-row tiles of the factor block handled per warp (J block padded to MT * 8 rows of zeros).
+// (ncu of the previous version, profiles/r01_ncu_mode_dot_v3.txt: 800 warp instructions per 2 KB tile - runtime-
+//  predicated 8 x 8 unrolled loops - kept the issue slots 47 % busy with 4 warps per scheduler and DRAM at 27 %.)
+template <bool LAST, int MT>
+__global__ void __launch_bounds__(256, 3) mode_dot_small_kernel(const ModeSmallParams p) {
   extern __shared__ __align__(16) double msm[];
-  double* ms = msm;                                         // [<= 64 rows of this CTA's J block][SA]
-  const int j0 = blockIdx.y * 64;                           // J block of this CTA (grid.y = ceil(Jp / 64))
-  const int jrows = min(64, p.Jp - j0);
+  double* ms = msm;                                         // [MT * 8 rows of this CTA's J block][SA]
+  const int j0 = blockIdx.y * (MT * 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-  double* stages = msm + (size_t)min(p.Jp, 64) * p.SA + (size_t)warp * MS_STAGES * MS_STAGE_DOUBLES;   // warp-private ring
+  double* stages = msm + (size_t)(MT * 8) * p.SA + (size_t)warp * MS_STAGES * MS_STAGE_DOUBLES;   // warp-private ring
   const int I = p.I, J = p.J, SA = p.SA;
   const long long inner = p.inner, ncols = p.ncols;
-  for (int e = tid; e < jrows * SA; e += 256) {
+  for (int e = tid; e < MT * 8 * SA; e += 256) {
     const int jl = e / SA, k = e - jl * SA, j = j0 + jl;
     double v = 0.0;
     if (j < J && k < I) v = p.transpose_mat ? p.mat[(long long)k * J + j] : p.mat[(long long)j * I + k];
@@ -160,30 +163,28 @@ __global__ void __launch_bounds__(256, 2) mode_dot_small_kernel(const ModeSmallP
   }
   __syncthreads();                                          // the only CTA barrier
   const int nkb = (p.Ip + MS_KB - 1) / MS_KB;
-  const int mtiles = jrows / 8;
   const long long nblocks = (ncols + 7) >> 3;               // 8-column (LAST: 8-row) blocks
   const long long wstride = (long long)gridDim.x * MS_WARPS;
   const long long wb0 = (long long)blockIdx.x * MS_WARPS + warp;
-  const long long my_blocks = (nblocks > wb0) ? (nblocks - wb0 + wstride - 1) / wstride : 0;
-  const long long nq = my_blocks * nkb;
+  const int my_blocks = (nblocks > wb0) ? (int)((nblocks - wb0 + wstride - 1) / wstride) : 0;
+  const int nq = my_blocks * nkb;
   // per-lane generalised column of the LOAD side (advances by wstride * 8 per block) and of the STORE side
   const long long dq = (wstride * 8) / inner, dr = (wstride * 8) - dq * inner;
   long long lc = wb0 * 8 + (LAST ? 0 : 2 * tq), lo = LAST ? 0 : lc / inner, lci = LAST ? 0 : lc - lo * inner;   // load cursor
   long long sc = lc, so = lo, sci = lci;                                                                        // store cursor
-  int lkb = 0;
-  long long issued = 0;
+  int lkb = 0, issued = 0;
 
   auto issue = [&]() {
     if (issued < nq) {
-      double* st = stages + (size_t)(issued % MS_STAGES) * MS_STAGE_DOUBLES;
+      double* st = stages + (issued & (MS_STAGES - 1)) * MS_STAGE_DOUBLES;
       if (!LAST) {
         const bool cok = lc < ncols;
-        const double* src = p.t + (lo * I) * inner + lci;
+        const double* src = p.t + (lo * I + lkb * MS_KB) * inner + lci;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          const int kl = g + 8 * i, k = lkb * MS_KB + kl;
-          double* dst = st + kl * MS_LD_COLS + 2 * tq;
-          if (cok && k < I) cp_async16(dst, src + (long long)k * inner);
+          const int kl = g + 8 * i;
+          double* dst = st + kl * 8 + ((2 * tq) ^ (4 * ((kl >> 1) & 1)));
+          if (cok && lkb * MS_KB + kl < I) cp_async16(dst, src + (long long)kl * inner);
           else { dst[0] = 0.0; dst[1] = 0.0; }
         }
       } else {
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(256, 2) mode_dot_small_kernel(const ModeSmallP
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const int r = (lane >> 4) + 2 * i;
-          double* dst = st + r * MS_LD_K + 2 * kv;
+          double* dst = st + r * 32 + ((2 * kv) ^ (4 * (r & 3)));
           if (lc + r < ncols && k < I) cp_async16(dst, p.t + (lc + r) * I + k);
           else { dst[0] = 0.0; dst[1] = 0.0; }
         }
@@ -207,71 +208,82 @@ __global__ void __launch_bounds__(256, 2) mode_dot_small_kernel(const ModeSmallP
   };
 
   for (int q = 0; q < MS_STAGES - 1; q++) issue();
-  double acc[8][2];
+  double acc[MT][2];
 #pragma unroll
-  for (int i = 0; i < 8; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  for (int i = 0; i < MT; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
   int kb = 0;
   const uint32_t ms_u32 = (uint32_t)__cvta_generic_to_shared(ms) + (uint32_t)((g * SA + tq) * 8);
-  const uint32_t st_u32 = (uint32_t)__cvta_generic_to_shared(stages) + (uint32_t)((LAST ? g * MS_LD_K + tq : tq * MS_LD_COLS + g) * 8);
+  const uint32_t st_u32 = (uint32_t)__cvta_generic_to_shared(stages) +
+                          (uint32_t)((LAST ? g * 32 + tq : tq * 8 + (g ^ (4 * (tq >> 1)))) * 8);
   const uint32_t m_stride = (uint32_t)(SA * 64);
-  constexpr uint32_t s_step = LAST ? 32u : (uint32_t)(4 * MS_LD_COLS * 8);
-  for (long long q = 0; q < nq; q++) {
+  const uint32_t a_swz = (uint32_t)(g & 3);
+  for (int q = 0; q < nq; q++) {
     cp_async_wait<MS_STAGES - 2>();
     __syncwarp();                             // tile q landed for every lane; the stage of tile q-1 is free
     issue();
-    const uint32_t s_base = st_u32 + (uint32_t)((q % MS_STAGES) * MS_STAGE_DOUBLES * 8);
+    const uint32_t s_base = st_u32 + (uint32_t)((q & (MS_STAGES - 1)) * MS_STAGE_DOUBLES * 8);
     const uint32_t m_base = ms_u32 + (uint32_t)(kb * MS_KB * 8);
     const int ksteps = min(MS_KB, p.Ip - kb * MS_KB) >> 2;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ks++) {
+      const double sf = lds_f64(LAST ? s_base + (((uint32_t)ks ^ a_swz) << 5) : s_base + (uint32_t)(ks << 8));
 #pragma unroll
-    for (int ks = 0; ks < MS_KB / 4; ks++) {
-      if (ks < ksteps) {
-        const double sf = lds_f64(s_base + ks * s_step);
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          if (i < mtiles) {
-            const double mf = lds_f64(m_base + ks * 32 + i * m_stride);
-            if (LAST) dmma884(acc[i][0], acc[i][1], sf, mf);
-            else dmma884(acc[i][0], acc[i][1], mf, sf);
-          }
-        }
+      for (int i = 0; i < MT; i++) {
+        const double mf = lds_f64(m_base + ks * 32 + i * m_stride);
+        if (LAST) dmma884(acc[i][0], acc[i][1], sf, mf);
+        else dmma884(acc[i][0], acc[i][1], mf, sf);
       }
     }
     if (++kb == nkb) {
       kb = 0;
       if (!LAST) {
         if (sc < ncols) {
-          double* dst = p.out + (so * J) * inner + sci;
+          double* dst = p.out + (so * J + j0 + g) * inner + sci;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int j = j0 + i * 8 + g;
-            if (i < mtiles && j < J) *reinterpret_cast<double2*>(dst + (long long)j * inner) = make_double2(acc[i][0], acc[i][1]);
-          }
+          for (int i = 0; i < MT; i++)
+            if (j0 + i * 8 + g < J) *reinterpret_cast<double2*>(dst + (long long)(i * 8) * inner) = make_double2(acc[i][0], acc[i][1]);
         }
         sc += wstride * 8; so += dq; sci += dr;
         if (sci >= inner) { sci -= inner; ++so; }
       } else {
         const long long r = sc + g;
         if (r < ncols) {
-          double* dst = p.out + r * J;
+          double* dst = p.out + r * J + j0 + tq * 2;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
+          for (int i = 0; i < MT; i++) {
             const int j = j0 + i * 8 + tq * 2;
-            if (i < mtiles) {
-              if (!(J & 1) && j + 1 < J) *reinterpret_cast<double2*>(dst + j) = make_double2(acc[i][0], acc[i][1]);
-              else {
-                if (j < J) dst[j] = acc[i][0];
-                if (j + 1 < J) dst[j + 1] = acc[i][1];
-              }
+            if (!(J & 1) && j + 1 < J) *reinterpret_cast<double2*>(dst + i * 8) = make_double2(acc[i][0], acc[i][1]);
+            else {
+              if (j < J) dst[i * 8] = acc[i][0];
+              if (j + 1 < J) dst[i * 8 + 1] = acc[i][1];
             }
           }
         }
         sc += wstride * 8;
       }
 #pragma unroll
-      for (int i = 0; i < 8; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+      for (int i = 0; i < MT; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
     }
   }
   cp_async_wait<0>();
+}
+
+template <bool LAST, int MT>
+static cudaError_t launch_mode_small(const ModeSmallParams& p, int sms, cudaStream_t st) {
+  auto kern = mode_dot_small_kernel<LAST, MT>;
+  const size_t smem = ((size_t)(MT * 8) * p.SA + (size_t)MS_WARPS * MS_STAGES * MS_STAGE_DOUBLES) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int jblocks = (p.Jp + MT * 8 - 1) / (MT * 8);
+  const long long nchunks = (p.ncols + 63) / 64;              // 8 warps x 8-column blocks per CTA pass
+  const int per_sm = std::max(1, std::min(3, (int)((224 * 1024) / (smem + 1024))));
+  const int gx = (int)std::min<long long>(nchunks, std::max(1, sms * per_sm / jblocks));
+  kern<<<dim3(gx, jblocks), 256, smem, st>>>(p);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1046,19 +1058,14 @@ int ffgp_mode_dot_f64(const double* t, const double* mat, double* out, long long
     p.t = t; p.mat = mat; p.out = out; p.ncols = ncols; p.inner = inner; p.I = I; p.J = J; p.transpose_mat = transpose_mat;
     p.Ip = (I + 3) & ~3; p.Jp = (J + 7) & ~7;
     p.SA = p.Ip + ((4 - p.Ip % 16) + 16) % 16;             // smallest stride >= Ip with SA = 4 (mod 16)
-    const size_t smem = ((size_t)std::min(p.Jp, 64) * p.SA + (size_t)MS_WARPS * MS_STAGES * MS_STAGE_DOUBLES) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-      FFGP_CUDA(cudaFuncSetAttribute(mode_dot_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      FFGP_CUDA(cudaFuncSetAttribute(mode_dot_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      attr = true;
-    }
-    const long long nchunks = (ncols + 63) / 64;                // 8 warps x 8-column blocks per CTA pass
-    const int per_sm = std::max(1, std::min(2, (int)((220 * 1024) / smem)));
-    const int gx = (int)std::min<long long>(nchunks, std::max(1, ms_num_sms() * per_sm / ((p.Jp + 63) / 64)));
-    const dim3 grid(gx, (p.Jp + 63) / 64);
-    if (inner == 1) mode_dot_small_kernel<true><<<grid, 256, smem, st>>>(p);
-    else mode_dot_small_kernel<false><<<grid, 256, smem, st>>>(p);
+    const int sms = ms_num_sms();
+    const bool last = inner == 1;
+    cudaError_t e;
+    if (p.Jp <= 8) e = last ? launch_mode_small<true, 1>(p, sms, st) : launch_mode_small<false, 1>(p, sms, st);
+    else if (p.Jp <= 16) e = last ? launch_mode_small<true, 2>(p, sms, st) : launch_mode_small<false, 2>(p, sms, st);
+    else if (p.Jp <= 32) e = last ? launch_mode_small<true, 4>(p, sms, st) : launch_mode_small<false, 4>(p, sms, st);
+    else e = last ? launch_mode_small<true, 8>(p, sms, st) : launch_mode_small<false, 8>(p, sms, st);
+    FFGP_CUDA(e);
     ++ffgp::g_launches;
     FFGP_CUDA(cudaGetLastError());
     return 0;
