@@ -14,6 +14,24 @@ namespace ffgp {
 
 thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;   // kernels launched by this library (bench.py reports it as gpu_launches)
+// FFGP_TRACE=1: a timing event after every level-3 launch of a dense evaluation, dumped (with a host sync) by
+// ffgp_trace_dump() - the timeline tool behind profiles/r01_timeline_*.txt.  Never enabled in production.
+struct TraceRec { const char* what; int a, b; void* stream; cudaEvent_t ev; };
+static TraceRec g_trace[8192];
+static int g_ntrace = 0;
+static int trace_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_TRACE"); v = e ? atoi(e) : 0; }
+  return v;
+}
+static void trace_mark(const char* what, int a, int b, cudaStream_t st) {
+  if (!trace_on() || g_ntrace >= 8192) return;
+  TraceRec& r = g_trace[g_ntrace++];
+  r.what = what; r.a = a; r.b = b; r.stream = (void*)st;
+  cudaEventCreate(&r.ev);
+  cudaEventRecord(r.ev, st);
+}
+
 int fail(int code, const char* fmt, const char* a = "") {
   snprintf(g_err, sizeof(g_err), fmt, a);
   return code;
@@ -55,6 +73,7 @@ static bool use_tma_gemm() {
 }
 
 static thread_local int g_cta_cap = 0;   // > 0: see gemm()
+static thread_local const char* g_trace_label = "gemm";
 
 static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long long sA, const double* B, int ldb,
                         long long sB, double* C, int ldc, long long sC, int M, int N, int K, double alpha, double beta,
@@ -106,14 +125,16 @@ static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long
     const long long tiles = (lower_only ? tm * (tm + 1) / 2 : tm * tn) * batch;
     if (tiles < (long long)num_sms()) big = false;     // 64x64 tiles: 4x the CTAs for the small levels
   }
-  if (big && use_tma_gemm()) {
-    const cudaError_t e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st);
-    if (e != cudaErrorNotSupported) return e;
+  cudaError_t e = cudaErrorNotSupported;
+  if (big && use_tma_gemm()) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st);
+  if (e == cudaErrorNotSupported) {
+    if (a_kmaj && b_kmaj) e = launch_gemm<true, true>(p, batch, big, st);
+    else if (a_kmaj && !b_kmaj) e = launch_gemm<true, false>(p, batch, big, st);
+    else if (!a_kmaj && b_kmaj) e = launch_gemm<false, true>(p, batch, big, st);
+    else e = launch_gemm<false, false>(p, batch, big, st);
   }
-  if (a_kmaj && b_kmaj) return launch_gemm<true, true>(p, batch, big, st);
-  if (a_kmaj && !b_kmaj) return launch_gemm<true, false>(p, batch, big, st);
-  if (!a_kmaj && b_kmaj) return launch_gemm<false, true>(p, batch, big, st);
-  return launch_gemm<false, false>(p, batch, big, st);
+  trace_mark(g_trace_label, M, N * 100000 + K, st);
+  return e;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,6 +241,7 @@ static cudaError_t factor_rec(const FactorCtx& c, int off, int n) {
     potrf_trtri_base_kernel<<<c.batch, 256, BASE_SMEM, c.st>>>(c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part,
                                                                c.nblk, off / BASE_N, c.info, off);
     ++g_launches;
+    trace_mark("base", off, 0, c.st);
     return cudaGetLastError();
   }
   // split at a multiple of 128: top half gets the larger power-of-two-ish share
@@ -318,6 +340,7 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
   for (int k = 0; k + 1 < nblk; k++) {
     const int rows1 = np - (k + 1) * NB;            // rows below block row k
     // (a) rank-NB update of block column k+1
+    g_trace_label = "a:colupd";
     if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1), c.ld,
                   c.sb, rows1, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
     cudaStream_t ps = c.st;
@@ -327,13 +350,16 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
       ps = aux->st;
     }
     // (b) panel k+1: diagonal block (factor + inverse), then TRSM of the rows below it
+    g_trace_label = "b:panel";
     if ((e = factor_rec(aux ? ca : c, (k + 1) * NB, NB)) != cudaSuccess) return e;
     const int rows2 = np - (k + 2) * NB;
     if (rows2 > 0) {
+      g_trace_label = "b:trsm";
       if ((e = gemm(true, true, c.A + at(k + 2, k + 1), c.ld, c.sb, c.M + at(k + 1, k + 1), c.ld, c.sb,
                     c.L + at(k + 2, k + 1), c.ld, c.sb, rows2, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, ps)) != cudaSuccess)
         return e;
       // (c) rest of the trailing update of step k (independent of the panel): lower tiles of A[k+2:, k+2:]
+      g_trace_label = "c:syrk";
       if ((e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 2, k), c.ld, c.sb, c.A + at(k + 2, k + 2), c.ld,
                     c.sb, rows2, rows2, NB, -1.0, 1.0, 1, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
     }
@@ -400,7 +426,8 @@ static cudaError_t trtri_bottom_up_range(const FactorCtx& c, int off, int n) {
 // which is final at the midpoint.  Streams: panel chain (highest priority) > trailing updates > background W.
 static int bg_cta_cap() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("FFGP_BG_CAP"); v = e ? atoi(e) : (num_sms() * 2) / 3; }
+  // default 0 = no cap (measured at N=8192: bands of 98 CTAs 22.2 ms/eval vs 21.6 ms uncapped)
+  if (v < 0) { const char* e = getenv("FFGP_BG_CAP"); v = e ? atoi(e) : 0; }
   return v;
 }
 
@@ -429,11 +456,24 @@ static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int 
     if ((e2 = cudaEventRecord(aux->ev_half, cb.st)) != cudaSuccess) return e2;
     if ((e2 = cudaStreamWaitEvent(cg.st, aux->ev_half, 0)) != cudaSuccess) return e2;
     g_cta_cap = bg_cta_cap();
+    g_trace_label = "bg:trtri";
     e2 = trtri_bottom_up_range(cg, 0, h);
     // W = L21 M11 -> A21 (dead: every block column of the leading half has been solved)
-    if (e2 == cudaSuccess)
-      e2 = gemm(true, false, c.L + o21, c.ld, c.sb, c.M, c.ld, c.sb, c.A + o21, c.ld, c.sb, h, h, h, 1.0, 0.0, 0, K_GE_COL,
-                c.batch, cg.st);
+    // W = L21 M11 -> A21 (dead: every block column of the leading half has been solved), in K chunks of 512 with
+    // beta = 1 accumulation: one launch with K up to h keeps every SM busy for ~100 us per tile and stalled the panel
+    // chain by 1.7 ms (profiles/r01_timeline_c2_v1.txt, steps 19-20); with 512-deep tiles an SM frees up every ~7 us.
+    g_trace_label = "bg:W";
+    const int KC = 512;
+    for (int s0 = 0; s0 < h && e2 == cudaSuccess; s0 += KC) {
+      const int kc = std::min(KC, h - s0);
+      // columns [s0, s0 + kc): first touch, the chunk's own lower-triangular block of M11 (K range starts at the column)
+      e2 = gemm(true, false, c.L + o21 + s0, c.ld, c.sb, c.M + (long long)s0 * c.ld + s0, c.ld, c.sb, c.A + o21 + s0, c.ld, c.sb,
+                h, kc, kc, 1.0, 0.0, 0, K_GE_COL, c.batch, cg.st);
+      // columns [0, s0): accumulate this chunk's full-depth contribution
+      if (s0 > 0 && e2 == cudaSuccess)
+        e2 = gemm(true, false, c.L + o21 + s0, c.ld, c.sb, c.M + (long long)s0 * c.ld, c.ld, c.sb, c.A + o21, c.ld, c.sb, h, s0,
+                  kc, 1.0, 1.0, 0, K_FULL, c.batch, cg.st);
+    }
     g_cta_cap = 0;
     return e2;
   };
@@ -443,6 +483,7 @@ static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int 
   *done = true;
   if (stop_after == 1) return cudaSuccess;
   // inverse of the trailing half, then the one product that needs both halves
+  g_trace_label = "post:trtri";
   if ((e = trtri_bottom_up_range(c, h, h)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(aux->ev_bg, cg.st)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(c.st, aux->ev_bg, 0)) != cudaSuccess) return e;
@@ -555,6 +596,21 @@ using namespace ffgp;
 extern "C" {
 
 int ffgp_version(void) { return FFGP_VERSION; }
+
+// Debug only (FFGP_TRACE=1): synchronise and print "<ms since first mark> <stream> <label> <a> <b>" per recorded launch.
+int ffgp_trace_dump(void) {
+  if (!trace_on() || g_ntrace == 0) return 0;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < g_ntrace; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace[0].ev, g_trace[i].ev);
+    printf("TRACE %9.3f %p %-12s %d %d\n", ms, g_trace[i].stream, g_trace[i].what, g_trace[i].a, g_trace[i].b);
+  }
+  for (int i = 0; i < g_ntrace; i++) cudaEventDestroy(g_trace[i].ev);
+  const int n = g_ntrace;
+  g_ntrace = 0;
+  return n;
+}
 unsigned long long ffgp_launch_count(void) { return g_launches; }
 const char* ffgp_last_error_string(void) { return g_err; }
 

@@ -534,6 +534,24 @@ __global__ void __launch_bounds__(256) colsum_weighted_kernel(const double* __re
   for (int q = 0; q < QMAX; q++) acc[q] = 0.0;
   const int p_lo = lower ? c0 : 0;
   int pp = p_lo + warp;
+  // 16 independent row loads in flight per warp (32 KB per CTA): the first column block of a lower-triangular Mat
+  // streams all P rows through ONE CTA, which with 4 loads in flight was latency-bound at 5 GB/s (0.46 ms at
+  // N = 8192, profiles/r01_metrics_c2_v1.txt)
+  for (; pp + 120 < P; pp += 128) {
+    double mv[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) mv[u] = mat[(long long)(pp + 8 * u) * ld + c0 + lane];
+    if (square) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) acc[0] = fma(mv[u], mv[u], acc[0]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 16; u++)
+#pragma unroll
+        for (int q = 0; q < QMAX; q++)
+          if (q < Q) acc[q] = fma(mv[u], w[(long long)(pp + 8 * u) * ldw + q], acc[q]);
+    }
+  }
   for (; pp + 24 < P; pp += 32) {               // 4 independent row loads in flight per warp
     double mv[4];
 #pragma unroll

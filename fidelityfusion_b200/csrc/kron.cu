@@ -354,96 +354,104 @@ __global__ void __launch_bounds__(256) mode_gram_kernel(const double* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming mode Gram (replaces mode_gram_kernel for 16-byte-alignable layouts; that kernel reached 3-7 % of HBM,
-// profiles/r01_kron_bench_v1.txt).  G tile of TILE x TILE (32 or 64) per CTA, the column range split into
-// `nslices` interleaved chunk sets; X and Y stream through a 4-stage cp.async ring of 32-column chunks; the 8 warps
-// split the chunk's k-steps (TILE = 32: 8 ways, TILE = 64: 2 x 2 warp tiles x 2 ways) and are summed in a fixed
-// order at the end; slices are summed in index order by gram_reduce_kernel (deterministic, no atomics).
-//   INNER1 == false: inner even: stage = [2 TILE rows (X rows, then Y rows)][32 columns], stride 36;
-//   INNER1 == true : inner == 1: stage = [32 columns][X: TILE | Y: TILE], row stride 2 (TILE + 4) + 4.
+// Streaming mode Gram (replaces mode_gram_kernel for 16-byte-alignable layouts; that kernel reached 3-7 % of HBM and
+// a CTA-synchronous cp.async version 50 %, profiles/r01_kron_bench_v{1,2}.txt).  Same structure as
+// mode_dot_small_kernel: no CTA barrier in the loop, every warp streams its own 8-column blocks of X and Y through a
+// private 4-stage cp.async ring and accumulates a whole (8 MT) x (8 MT) tile of G in registers; grid.z / grid.y pick
+// the 32 x 32 tile of G, grid.x the interleaved slice of the column range.  Warps are summed in fixed order at the
+// end and slices in index order by gram_reduce_kernel (deterministic, no atomics).
+// Stage = X tile | Y tile, 256 doubles each, XOR-swizzled:
+//   INNER1 == false (inner even): element (row r, col c)  at r * 8  + (c ^ (4 * ((r >> 1) & 1)))
+//   INNER1 == true  (inner == 1): element (col c, row a)  at c * 32 + (a ^ (4 * (c & 3)))
 // ---------------------------------------------------------------------------------------------
-constexpr int GS_CH = 32, GS_STAGES = 4;
+constexpr int GS_STAGES = 3, GS_STAGE_DOUBLES = 512, GS_WARPS = 8;   // 12 KB per warp, 96 KB per CTA: 2 CTAs / SM
 
-template <int TILE, bool INNER1>
-__global__ void __launch_bounds__(256) mode_gram_stream_kernel(const double* __restrict__ X, const double* __restrict__ Y,
-                                                               double* __restrict__ part, long long ncols, long long inner,
-                                                               int Ja, int Jb) {
-  constexpr int SA = TILE + 4;                       // INNER1 operand width
-  constexpr int RS1 = 2 * SA + 4;                    // INNER1 row stride (= 12 mod 16)
-  constexpr int RS0 = GS_CH + 4;                     // !INNER1 row stride (= 4 mod 16)
-  constexpr int STAGE = INNER1 ? GS_CH * RS1 : 2 * TILE * RS0;
-  constexpr int WK = (TILE == 32) ? 8 : 2;
+template <bool INNER1, int MT>
+__global__ void __launch_bounds__(256, 2) mode_gram_stream_kernel(const double* __restrict__ X, const double* __restrict__ Y,
+                                                                  double* __restrict__ part, long long ncols, long long inner,
+                                                                  int Ja, int Jb) {
   extern __shared__ __align__(16) double gsm2[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-  const int wm = (TILE == 32) ? 0 : (warp & 1), wn = (TILE == 32) ? 0 : ((warp >> 1) & 1), wk = (TILE == 32) ? warp : (warp >> 2);
-  const int a0 = blockIdx.z * TILE, b0 = blockIdx.y * TILE;
-  const long long nchunks = (ncols + GS_CH - 1) / GS_CH;
-  const long long my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int a0 = blockIdx.z * 32, b0 = blockIdx.y * 32;
+  double* stages = gsm2 + (size_t)warp * GS_STAGES * GS_STAGE_DOUBLES;
+  const long long nblocks = (ncols + 7) >> 3;
+  const long long wstride = (long long)gridDim.x * GS_WARPS;
+  const long long wb0 = (long long)blockIdx.x * GS_WARPS + warp;
+  const int nq = (nblocks > wb0) ? (int)((nblocks - wb0 + wstride - 1) / wstride) : 0;
+  const long long dq = (wstride * 8) / inner, dr = (wstride * 8) - dq * inner;
+  long long lc = wb0 * 8 + (INNER1 ? 0 : 2 * tq), lo = INNER1 ? 0 : lc / inner, lci = INNER1 ? 0 : lc - lo * inner;
+  int issued = 0;
 
-  auto issue = [&](long long q) {
-    if (q < my_chunks) {
-      const long long c0 = (blockIdx.x + q * gridDim.x) * GS_CH;
-      double* st = gsm2 + (size_t)(q % GS_STAGES) * STAGE;
+  auto issue = [&]() {
+    if (issued < nq) {
+      double* st = stages + (issued % GS_STAGES) * GS_STAGE_DOUBLES;
       if (!INNER1) {
-        const int cv = tid & 15;
-        const long long c = c0 + 2 * cv;
-        const bool cok = c < ncols;
-        const long long o = cok ? c / inner : 0, ci = cok ? c - o * inner : 0;
+        const bool cok = lc < ncols;
 #pragma unroll
-        for (int i = 0; i < TILE / 8; i++) {
-          const int r = (tid >> 4) + 16 * i;                         // 0 .. 2 TILE - 1
-          const bool isY = r >= TILE;
-          const int row = isY ? b0 + r - TILE : a0 + r, J = isY ? Jb : Ja;
-          double* dst = st + r * RS0 + 2 * cv;
-          if (cok && row < J) cp_async16(dst, (isY ? Y : X) + (o * J + row) * inner + ci);
-          else { dst[0] = 0.0; dst[1] = 0.0; }
+        for (int i = 0; i < MT; i++) {
+          const int r = g + 8 * i;                                           // row of the 8 MT-row tile
+          const int swz = (2 * tq) ^ (4 * ((r >> 1) & 1));
+          double* dx = st + r * 8 + swz;
+          double* dy = dx + 256;
+          if (cok && a0 + r < Ja) cp_async16(dx, X + (lo * Ja + a0 + r) * inner + lci);
+          else { dx[0] = 0.0; dx[1] = 0.0; }
+          if (cok && b0 + r < Jb) cp_async16(dy, Y + (lo * Jb + b0 + r) * inner + lci);
+          else { dy[0] = 0.0; dy[1] = 0.0; }
         }
       } else {
+        // 8 columns x (8 MT) rows per operand: 4 MT 16-byte vectors per column
 #pragma unroll
-        for (int i = 0; i < TILE / 8; i++) {
-          const int v = tid + 256 * i;
-          const int vv = v % TILE, r = v / TILE;                     // TILE vectors per column row: X half, Y half
-          const bool isY = vv >= TILE / 2;
-          const int e = 2 * (vv % (TILE / 2));
-          const int J = isY ? Jb : Ja, j = (isY ? b0 : a0) + e;
-          double* dst = st + r * RS1 + (isY ? SA : 0) + e;
-          if (c0 + r < ncols && j < J) cp_async16(dst, (isY ? Y : X) + (c0 + r) * J + j);
-          else { dst[0] = 0.0; dst[1] = 0.0; }
+        for (int i = 0; i < MT; i++) {
+          const int v = lane + 32 * i;
+          const int c = v / (4 * MT), e = 2 * (v % (4 * MT));
+          const int off = c * 32 + (e ^ (4 * (c & 3)));
+          double* dx = st + off;
+          double* dy = dx + 256;
+          if (lc + c < ncols && a0 + e < Ja) cp_async16(dx, X + (lc + c) * Ja + a0 + e);
+          else { dx[0] = 0.0; dx[1] = 0.0; }
+          if (lc + c < ncols && b0 + e < Jb) cp_async16(dy, Y + (lc + c) * Jb + b0 + e);
+          else { dy[0] = 0.0; dy[1] = 0.0; }
         }
       }
+      ++issued;
+      lc += wstride * 8;
+      if (!INNER1) { lo += dq; lci += dr; if (lci >= inner) { lci -= inner; ++lo; } }
     }
     cp_async_commit();
   };
 
-  for (int q = 0; q < GS_STAGES - 1; q++) issue(q);
-  double acc[4][4][2];
+  for (int q = 0; q < GS_STAGES - 1; q++) issue();
+  double acc[MT][MT][2];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < MT; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-  for (long long q = 0; q < my_chunks; q++) {
+    for (int j = 0; j < MT; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  for (int q = 0; q < nq; q++) {
     cp_async_wait<GS_STAGES - 2>();
-    __syncthreads();
-    issue(q + GS_STAGES - 1);
-    const double* st = gsm2 + (size_t)(q % GS_STAGES) * STAGE;
+    __syncwarp();
+    issue();
+    const double* st = stages + (q % GS_STAGES) * GS_STAGE_DOUBLES;
 #pragma unroll
-    for (int kq = 0; kq < GS_CH / 4 / WK; kq++) {
-      const int kc = (kq * WK + wk) * 4;
-      double af[4], bf[4];
+    for (int ks = 0; ks < 2; ks++) {
+      double af[MT], bf[MT];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < MT; i++) {
         if (!INNER1) {
-          af[i] = st[(wm * 32 + i * 8 + g) * RS0 + kc + tq];
-          bf[i] = st[(TILE + wn * 32 + i * 8 + g) * RS0 + kc + tq];
+          const int r = i * 8 + g, c = ks * 4 + tq;
+          const int off = r * 8 + (c ^ (4 * ((r >> 1) & 1)));
+          af[i] = st[off];
+          bf[i] = st[256 + off];
         } else {
-          af[i] = st[(kc + tq) * RS1 + wm * 32 + i * 8 + g];
-          bf[i] = st[(kc + tq) * RS1 + SA + wn * 32 + i * 8 + g];
+          const int c = ks * 4 + tq, r = i * 8 + g;
+          const int off = c * 32 + (r ^ (4 * (c & 3)));
+          af[i] = st[off];
+          bf[i] = st[256 + off];
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < MT; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < MT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
@@ -451,28 +459,40 @@ __global__ void __launch_bounds__(256) mode_gram_stream_kernel(const double* __r
   // cross-warp sum in fixed order through shared memory: red[warp][32][34]
   double* red = gsm2;
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < MT; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < MT; j++) {
       double* d = red + (size_t)warp * 32 * 34 + (i * 8 + g) * 34 + j * 8 + tq * 2;
       d[0] = acc[i][j][0];
       d[1] = acc[i][j][1];
     }
   __syncthreads();
   double* dst = part + (long long)blockIdx.x * Ja * Jb;
-  for (int e = tid; e < TILE * TILE; e += 256) {
-    const int r = e / TILE, c = e - r * TILE;
+  for (int e = tid; e < (8 * MT) * (8 * MT); e += 256) {
+    const int r = e / (8 * MT), c = e - r * (8 * MT);
     const int a = a0 + r, b = b0 + c;
     if (a < Ja && b < Jb) {
       double v = 0.0;
 #pragma unroll
-      for (int k = 0; k < WK; k++) {
-        const int wsrc = (TILE == 32) ? k : (k * 4 + (c >> 5) * 2 + (r >> 5));
-        v += red[(size_t)wsrc * 32 * 34 + (r & 31) * 34 + (c & 31)];
-      }
+      for (int k = 0; k < GS_WARPS; k++) v += red[(size_t)k * 32 * 34 + r * 34 + c];
       dst[(long long)a * Jb + b] = v;
     }
   }
+}
+
+template <bool INNER1, int MT>
+static cudaError_t launch_gram_stream(const double* X, const double* Y, double* part, long long ncols, long long inner, int Ja,
+                                      int Jb, int ns, cudaStream_t st) {
+  const size_t smem = std::max((size_t)GS_WARPS * GS_STAGES * GS_STAGE_DOUBLES, (size_t)GS_WARPS * 32 * 34) * sizeof(double);
+  auto kern = mode_gram_stream_kernel<INNER1, MT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  kern<<<dim3(ns, (Jb + 31) / 32, (Ja + 31) / 32), 256, smem, st>>>(X, Y, part, ncols, inner, Ja, Jb);
+  return cudaGetLastError();
 }
 
 __global__ void gram_reduce_kernel(const double* __restrict__ part, int nslices, long long nelem, double* __restrict__ out) {
@@ -481,22 +501,6 @@ __global__ void gram_reduce_kernel(const double* __restrict__ part, int nslices,
   double s = 0.0;
   for (int z = 0; z < nslices; z++) s += part[(long long)z * nelem + i];
   out[i] = s;
-}
-
-template <int TILE, bool INNER1>
-static cudaError_t launch_gram_stream(const double* X, const double* Y, double* part, long long ncols, long long inner, int Ja,
-                                      int Jb, int ns, cudaStream_t st) {
-  constexpr int STAGE = INNER1 ? GS_CH * (2 * (TILE + 4) + 4) : 2 * TILE * (GS_CH + 4);
-  const size_t smem = std::max((size_t)GS_STAGES * STAGE, (size_t)8 * 32 * 34) * sizeof(double);
-  auto kern = mode_gram_stream_kernel<TILE, INNER1>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  kern<<<dim3(ns, (Jb + TILE - 1) / TILE, (Ja + TILE - 1) / TILE), 256, smem, st>>>(X, Y, part, ncols, inner, Ja, Jb);
-  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1096,10 +1100,9 @@ static bool gram_stream_ok(const void* X, const void* Y, long long inner, int Ja
 
 static int gram_slices(long long ncols, int Ja, int Jb, bool stream) {
   if (stream) {
-    const int tile = (Ja <= 32 && Jb <= 32) ? 32 : 64;
-    const long long tiles = (long long)((Ja + tile - 1) / tile) * ((Jb + tile - 1) / tile);
-    const long long nchunks = (ncols + GS_CH - 1) / GS_CH;
-    const long long want = std::max<long long>(1, ((long long)ms_num_sms() * (tile == 32 ? 2 : 1)) / tiles);
+    const long long tiles = (long long)((Ja + 31) / 32) * ((Jb + 31) / 32);
+    const long long nchunks = (ncols + 63) / 64;                 // 8 warps x 8-column blocks per CTA pass
+    const long long want = std::max<long long>(1, ((long long)ms_num_sms() * 2) / tiles);
     return (int)std::max<long long>(1, std::min(want, nchunks));
   }
   const long long tiles = (long long)((Ja + MG_T - 1) / MG_T) * ((Jb + MG_T - 1) / MG_T);
@@ -1124,12 +1127,15 @@ int ffgp_mode_gram_f64(const double* X, const double* Y, double* G, long long ou
   const bool stream_path = gram_stream_ok(X, Y, inner, Ja, Jb);
   const int ns = gram_slices(ncols, Ja, Jb, stream_path);
   if (stream_path) {
-    const bool small = Ja <= 32 && Jb <= 32;
+    const int jm = std::min(32, std::max(Ja, Jb));
+    double* pt = (double*)scratch;
     cudaError_t e;
-    if (inner == 1) e = small ? launch_gram_stream<32, true>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st)
-                              : launch_gram_stream<64, true>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st);
-    else e = small ? launch_gram_stream<32, false>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st)
-                   : launch_gram_stream<64, false>(X, Y, (double*)scratch, ncols, inner, Ja, Jb, ns, st);
+    if (inner == 1) e = jm <= 8 ? launch_gram_stream<true, 1>(X, Y, pt, ncols, inner, Ja, Jb, ns, st)
+                      : jm <= 16 ? launch_gram_stream<true, 2>(X, Y, pt, ncols, inner, Ja, Jb, ns, st)
+                                 : launch_gram_stream<true, 4>(X, Y, pt, ncols, inner, Ja, Jb, ns, st);
+    else e = jm <= 8 ? launch_gram_stream<false, 1>(X, Y, pt, ncols, inner, Ja, Jb, ns, st)
+             : jm <= 16 ? launch_gram_stream<false, 2>(X, Y, pt, ncols, inner, Ja, Jb, ns, st)
+                        : launch_gram_stream<false, 4>(X, Y, pt, ncols, inner, Ja, Jb, ns, st);
     FFGP_CUDA(e);
   } else {
     long long cps = (ncols + ns - 1) / ns;
