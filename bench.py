@@ -158,6 +158,62 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def kron_numbers(torch):
+    """Kronecker / coupling half of the path (BASELINE configs 3 and 4): HBM-bound mode products and the whole HOGP
+    loss+gradient step at the C4 shape 128 x 32 x 32 x 16.  CUDA events, median of 7, L2 evicted by a 512 MB read
+    between repetitions.  Algorithmic bytes per mode product: 16 B per tensor element + the factor."""
+    from fidelityfusion_b200 import tensorly_compat as tl
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    hbm = 6457.7
+    try:
+        hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+    except Exception:
+        pass
+    flush = torch.zeros(512 << 20, dtype=torch.uint8, device='cuda').view(torch.int64)
+
+    def med(fn, reps=7):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2] * 1e-3
+
+    g = torch.Generator().manual_seed(4)
+    out = {'hbm_peak_gbs': hbm, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst copy figure)'}
+    for tag, n in (('c4_128x32x32x16', 128), ('large_1024x32x32x16', 1024)):
+        T = torch.randn(n, 32, 32, 16, generator=g, dtype=torch.float64).cuda()
+        row = {}
+        for mode in (1, 3):
+            I = T.shape[mode]
+            U = torch.randn(I, I, generator=g, dtype=torch.float64).cuda()
+            sec = med(lambda: tl._mode_dot_raw(T, U, mode, False))
+            gbs = (16 * T.numel() + 8 * I * I) / sec * 1e-9
+            row[f'mode_dot_mode{mode}'] = {'us': sec * 1e6, 'GBps': gbs, 'hbm_frac': gbs / hbm}
+        sec = med(lambda: tl._mode_gram_raw(T, T, 1))
+        row['mode_gram_mode1'] = {'us': sec * 1e6, 'GBps': 16 * T.numel() / sec * 1e-9, 'hbm_frac': 16 * T.numel() / sec * 1e-9 / hbm}
+        sec = med(lambda: T.clone())
+        row['torch_clone_same_bytes'] = {'us': sec * 1e6, 'GBps': 16 * T.numel() / sec * 1e-9}
+        out[tag] = row
+        del T
+    x = torch.rand(128, 5, generator=g, dtype=torch.float64).cuda()
+    Y = torch.randn(128, 32, 32, 16, generator=g, dtype=torch.float64).cuda()
+    h = HOGP({'fidelity_shapes': [torch.Size([32, 32, 16])]}).double().cuda()
+
+    def step():
+        h.zero_grad(set_to_none=True)
+        h.compute_loss(x, Y).backward()
+
+    out['hogp_c4_loss_grad_ms'] = med(step) * 1e3
+    K = torch.exp(-0.5 * torch.cdist(x, x) ** 2)
+    out['eigh_n128_ms'] = med(lambda: tl.eigh(K)) * 1e3
+    return out
+
+
 def measure_dgemm_peak(torch):
     """FP64 roofline denominator: cuBLAS DGEMM 8192^3 through torch.matmul, best of 10 (MEASURED_PEAKS.json
     has no fp64 entry)."""
@@ -185,6 +241,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--skip-batched', action='store_true')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--skip-kron', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 0)
     if args.impl == 'reference':
@@ -362,6 +419,11 @@ def main():
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    if world == 1 and not args.skip_kron:
+        try:
+            line['kron'] = kron_numbers(torch)
+        except Exception as e:                          # secondary numbers must never cost the headline line
+            line['kron'] = {'error': repr(e)[:300]}
     if batched is not None:
         batched['roofline_frac'] = batched['tflops_alg'] / world / peak_tflops if peak_tflops else None
         line['batched'] = batched
