@@ -34,13 +34,15 @@ class cigp(nn.Module):
         noise = self.log_beta.exp().pow(-1)
         fp = fused_or_none(self.kernel)
         diag = (noise + JITTER).reshape(1)
-        with torch.no_grad():
-            if fp is not None:
-                inv_ls, amp, clamp = fp
-                mean, cov = ops.dense_predict(x_train, y_train, x_test, inv_ls, amp, diag_add=diag, cov_offset=noise,
-                                              full_cov=True, clamp=clamp, cache=self.factor_cache,
-                                              cache_token=ops.state_token(self, x_train, y_train))
-            else:
+        if fp is not None:
+            # differentiable w.r.t. x_test when it requires grad (acquisition optimisers, DMF_acq.py:247-254);
+            # parameters and training data are constants of the posterior
+            inv_ls, amp, clamp = fp
+            mean, cov = ops.dense_predict(x_train, y_train, x_test, inv_ls.detach(), amp.detach(), diag_add=diag.detach(),
+                                          cov_offset=noise.detach(), full_cov=True, clamp=clamp, cache=self.factor_cache,
+                                          cache_token=ops.state_token(self, x_train, y_train))
+        else:
+            with torch.no_grad():
                 mean, cov = ops.dense_predict(None, y_train, None, None, None, diag_add=diag,
                                               sigma_add=self.kernel(x_train, x_train), Ks=self.kernel(x_train, x_test),
                                               Kss=self.kernel(x_test, x_test), cov_offset=noise, full_cov=True)

@@ -45,6 +45,10 @@ def lib():
     _sig(L.ffgp_kernel_matrix_f64, i, [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp])
     _sig(L.ffgp_kernel_matrix_bwd_scratch_bytes, sz, [i, i, i, i])
     _sig(L.ffgp_kernel_matrix_bwd_f64, i, [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp])
+    _sig(L.ffgp_kernel_matrix_bwd_x_scratch_bytes, sz, [i, i, i, i])
+    _sig(L.ffgp_kernel_matrix_bwd_x_f64, i, [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp])
+    _sig(L.ffgp_dense_predict_bwd_scratch_bytes, sz, [i, i, i, i])
+    _sig(L.ffgp_dense_predict_bwd_f64, i, [vp] * 6 + [i] * 7 + [vp, sz, vp, vp, sz, vp])
     _sig(L.ffgp_dense_workspace_bytes, sz, [i, i, i, i, i])
     _sig(L.ffgp_dense_nll_f64, i, [vp] * 6 + [i] * 7 + [vp, sz] + [vp] * 7 + [vp, vp])
     _sig(L.ffgp_dense_predict_f64, i, [vp] * 10 + [i] * 9 + [vp, sz] + [vp, vp, vp, vp])

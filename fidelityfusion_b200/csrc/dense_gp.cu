@@ -9,6 +9,7 @@
 #include "dense_kernels.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_tma.cuh"
+#include "xgrad_kernels.cuh"
 
 namespace ffgp {
 
@@ -846,6 +847,109 @@ int ffgp_potrf_trtri_f64(const double* A, int n, int batch, void* workspace, siz
       nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, 1, nullptr, logdet + b0);
       FFGP_LAUNCHED();
     }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Input-point gradients (acquisition optimisers: d posterior / d x*)
+// ---------------------------------------------------------------------------------------------
+static size_t xgrad_part_bytes(int R, int C, int d, int batch) {
+  return (size_t)batch * xgrad_splits(R, C, batch) * R * d * sizeof(double);
+}
+
+static int launch_xgrad(XGradParams p, int batch, double* out, int accumulate, cudaStream_t st) {
+  p.splits = xgrad_splits(p.R, p.C, batch);
+  xgrad_kernel<<<dim3((p.R + XG_WARPS - 1) / XG_WARPS, p.splits, batch), XG_WARPS * 32, 0, st>>>(p);
+  FFGP_LAUNCHED();
+  const long long rd = (long long)p.R * p.d;
+  xgrad_finish_kernel<<<dim3((unsigned)((rd + 255) / 256), batch), 256, 0, st>>>(p.part, p.splits, rd, out, accumulate);
+  FFGP_LAUNCHED();
+  return 0;
+}
+
+size_t ffgp_kernel_matrix_bwd_x_scratch_bytes(int n1, int n2, int d, int batch) {
+  if (n1 <= 0 || n2 <= 0 || d <= 0 || batch <= 0) return 0;
+  return std::max(xgrad_part_bytes(n1, n2, d, batch), xgrad_part_bytes(n2, n1, d, batch)) + 256;
+}
+
+int ffgp_kernel_matrix_bwd_x_f64(const double* x1, const double* x2, const double* inv_ls, const double* amp,
+                                 const double* gK, int n1, int n2, int d, int batch, int params_batched, double* g_x1,
+                                 double* g_x2, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!x1 || !x2 || !inv_ls || !amp || !gK || !scratch) return fail(-1, "ffgp_kernel_matrix_bwd_x_f64: null pointer");
+  if (n1 <= 0 || n2 <= 0 || d <= 0 || d > XG_DMAX || batch <= 0) return fail(-2, "ffgp_kernel_matrix_bwd_x_f64: bad size (d <= 64)");
+  if (scratch_bytes < ffgp_kernel_matrix_bwd_x_scratch_bytes(n1, n2, d, batch)) return fail(-3, "ffgp_kernel_matrix_bwd_x_f64: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  XGradParams p;
+  memset(&p, 0, sizeof(p));
+  p.w = inv_ls; p.sw = params_batched ? d : 0; p.amp = amp; p.samp = params_batched ? 1 : 0;
+  p.gK = gK; p.sgK = (long long)n1 * n2; p.gk_scale = 1.0; p.d = d; p.part = (double*)scratch;
+  int rc;
+  if (g_x1) {
+    p.xr = x1; p.xc = x2; p.sxr = (long long)n1 * d; p.sxc = (long long)n2 * d; p.R = n1; p.C = n2; p.ldr = n2; p.ldc = 1;
+    if ((rc = launch_xgrad(p, batch, g_x1, 0, st)) != 0) return rc;
+  }
+  if (g_x2) {
+    p.xr = x2; p.xc = x1; p.sxr = (long long)n2 * d; p.sxc = (long long)n1 * d; p.R = n2; p.C = n1; p.ldr = 1; p.ldc = n2;
+    if ((rc = launch_xgrad(p, batch, g_x2, 0, st)) != 0) return rc;
+  }
+  return 0;
+}
+
+size_t ffgp_dense_predict_bwd_scratch_bytes(int n, int d, int ns, int batch) {
+  if (n <= 0 || ns <= 0 || d <= 0 || batch <= 0) return 0;
+  return std::max(xgrad_part_bytes(ns, n, d, batch), xgrad_part_bytes(ns, ns, d, batch)) + 256;
+}
+
+int ffgp_dense_predict_bwd_f64(const double* x, const double* xs, const double* inv_ls, const double* amp,
+                               const double* g_mean, const double* g_cov, int n, int d, int D, int ns, int batch,
+                               int params_batched, int full_cov, void* workspace, size_t workspace_bytes, double* g_xs,
+                               void* scratch, size_t scratch_bytes, void* stream) {
+  if (!x || !xs || !inv_ls || !amp || !workspace || !g_xs || !scratch) return fail(-1, "ffgp_dense_predict_bwd_f64: null pointer");
+  if (!g_mean && !g_cov) return fail(-1, "ffgp_dense_predict_bwd_f64: neither g_mean nor g_cov given");
+  if (n <= 0 || D <= 0 || batch <= 0 || d <= 0 || d > XG_DMAX || ns <= 0) return fail(-2, "ffgp_dense_predict_bwd_f64: bad size (d <= 64)");
+  if (scratch_bytes < ffgp_dense_predict_bwd_scratch_bytes(n, d, ns, batch)) return fail(-3, "ffgp_dense_predict_bwd_f64: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  DenseWs w = layout_ws(n, d, D, ns, batch, (char*)workspace);
+  if (workspace_bytes < w.bytes) return fail(-3, "ffgp_dense_predict_bwd_f64: workspace too small");
+  if (batch > w.chunk) return fail(-4, "ffgp_dense_predict_bwd_f64: batch must fit one workspace chunk (the factor must be resident)");
+  const long long sM = (long long)w.np * w.np, sKx = (long long)w.np * w.nsp, sKxx = (long long)w.nsp * w.nsp;
+  const int Dw = w.gemm_rhs ? w.Dp : D;
+  XGradParams p;
+  memset(&p, 0, sizeof(p));
+  p.w = inv_ls; p.sw = params_batched ? d : 0; p.amp = amp; p.samp = params_batched ? 1 : 0; p.d = d;
+  p.part = (double*)scratch;
+  p.xr = xs; p.sxr = (long long)ns * d; p.R = ns;
+  p.xc = x; p.sxc = (long long)n * d; p.C = n;
+  if (g_mean) {                                    // d mean / d K* = alpha g_mean^T
+    p.lr_c = w.alpha; p.ld_lrc = Dw; p.s_lrc = (long long)w.np * Dw; p.lr_r = g_mean; p.lrD = D; p.s_lrr = (long long)ns * D;
+  }
+  int rc;
+  if (g_cov) {
+    // R = M^T V = Sigma^-1 K*  (into the dead K* buffer; the forward recomputes K* on every call)
+    FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.V, w.nsp, sKx, w.Kx, w.nsp, sKx, w.np, w.nsp, w.np, 1.0, 0.0, 0, K_GE_ROW,
+                   batch, st));
+    const double* T = w.Kx;
+    if (full_cov) {                                // d cov / d K* = -R (G + G^T)
+      dim3 blk(32, 8), grd((w.nsp + 31) / 32, (w.nsp + 7) / 8, batch);
+      sym_pad_kernel<<<grd, blk, 0, st>>>(g_cov, ns, (long long)ns * ns, w.Kxx, w.nsp, sKxx);
+      FFGP_LAUNCHED();
+      FFGP_CUDA(gemm(true, false, w.Kx, w.nsp, sKx, w.Kxx, w.nsp, sKxx, w.V, w.nsp, sKx, w.np, w.nsp, w.nsp, 1.0, 0.0, 0,
+                     K_FULL, batch, st));
+      T = w.V;
+    } else {                                       // d var_j / d K*[:, j] = -2 R[:, j] g_var[j]
+      p.colscale = g_cov;
+    }
+    p.gK = T; p.ldr = 1; p.ldc = w.nsp; p.sgK = sKx; p.gk_scale = full_cov ? -1.0 : -2.0;
+  }
+  if ((rc = launch_xgrad(p, batch, g_xs, 0, st)) != 0) return rc;
+  if (g_cov && full_cov) {                         // + d K(x*, x*) / d x*  with the symmetrised weights
+    XGradParams q;
+    memset(&q, 0, sizeof(q));
+    q.w = p.w; q.sw = p.sw; q.amp = p.amp; q.samp = p.samp; q.d = d; q.part = (double*)scratch;
+    q.xr = xs; q.xc = xs; q.sxr = q.sxc = (long long)ns * d; q.R = ns; q.C = ns;
+    q.gK = w.Kxx; q.ldr = w.nsp; q.ldc = 1; q.sgK = sKxx; q.gk_scale = 1.0;
+    if ((rc = launch_xgrad(q, batch, g_xs, 1, st)) != 0) return rc;
   }
   return 0;
 }

@@ -171,8 +171,21 @@ def dense_nll(x, y, inv_ls, amp, diag_add=None, sigma_add=None, clamp=False):
 
 def dense_predict(x, y, xs, inv_ls, amp, diag_add=None, sigma_add=None, Ks=None, Kss=None, cov_offset=None,
                   full_cov=True, want_cov=True, clamp=False, cache=None, cache_token=None):
-    """Posterior mean and (full or diagonal) covariance.  No autograd (the reference's gen-2023 forward runs under
-    no_grad, cigp.py:79; gen-2024 callers use it for prediction).  `cache`: a FactorCache to skip re-factorising."""
+    """Posterior mean and (full or diagonal) covariance.  `cache`: a FactorCache to skip re-factorising.
+    Differentiable w.r.t. the TEST points xs (what the acquisition optimisers need, DMF_acq.py:247-254) when grad mode
+    is on and xs.requires_grad; hyper-parameters and training data are constants of the posterior (the reference's
+    gen-2023 forward runs under no_grad, cigp.py:79; training differentiates the NLL, never the posterior)."""
+    if torch.is_grad_enabled() and amp is not None and xs is not None and xs.requires_grad:
+        args = dict(diag_add=diag_add, sigma_add=sigma_add, cov_offset=cov_offset, full_cov=full_cov, want_cov=want_cov,
+                    clamp=clamp, cache=cache, cache_token=cache_token)
+        mean, cov = _PredictDx.apply(xs, x, y, inv_ls, amp, args)
+        return mean, (cov if want_cov else None)
+    return _dense_predict_raw(x, y, xs, inv_ls, amp, diag_add, sigma_add, Ks, Kss, cov_offset, full_cov, want_cov, clamp,
+                              cache, cache_token)
+
+
+def _dense_predict_raw(x, y, xs, inv_ls, amp, diag_add=None, sigma_add=None, Ks=None, Kss=None, cov_offset=None,
+                       full_cov=True, want_cov=True, clamp=False, cache=None, cache_token=None, _keep=None):
     out_dtype = y.dtype
     x_, y_, il_, amp_, dg_, sg_, n, d, D, batch, pb, squeeze = _norm_batch(x, y, inv_ls, amp, diag_add, sigma_add)
     dev = y.device
@@ -218,12 +231,69 @@ def dense_predict(x, y, xs, inv_ls, amp, diag_add=None, sigma_add=None, Ks=None,
         check_info(info)
         if cache is not None:
             cache.mark_valid()
+    if cache is not None:
+        cache.generation += 1
+    if _keep is not None:                       # _PredictDx.backward needs the exact buffers of this call
+        _keep.update(ws=ws, wsb=wsb, xc=xc, xsc=xsc, ilc=ilc, ac=ac, dims=(n, d, D, ns, batch, pb), squeeze=squeeze,
+                     generation=cache.generation if cache is not None else None)
     mean = mean.to(out_dtype)
     cov = cov.to(out_dtype) if cov is not None else None
     if squeeze:
         mean = mean[0]
         cov = cov[0] if cov is not None else None
     return mean, cov
+
+
+class _PredictDx(torch.autograd.Function):
+    """Posterior (mean, cov) as a function of the test points.  backward() is ONE C call
+    (ffgp_dense_predict_bwd_f64) on the workspace the forward left behind; if anything else used that workspace in
+    between, the forward is replayed first (cheap: the factor is cached)."""
+
+    @staticmethod
+    def forward(ctx, xs, x, y, inv_ls, amp, args):
+        keep = {}
+        with torch.no_grad():
+            mean, cov = _dense_predict_raw(x, y, xs, inv_ls, amp, _keep=keep, **args)
+        ctx.keep, ctx.args = keep, args
+        ctx.inputs = (x, y, xs.detach(), inv_ls, amp)
+        ctx.xs_dtype = xs.dtype
+        if cov is None:
+            cov = mean.new_zeros(())
+            ctx.mark_non_differentiable(cov)
+        return mean, cov
+
+    @staticmethod
+    def backward(ctx, g_mean, g_cov):
+        keep, args = ctx.keep, ctx.args
+        cache = args['cache']
+        x, y, xs, inv_ls, amp = ctx.inputs
+        stale = cache is None or keep.get('used') or cache.generation != keep['generation'] or cache.buf is not keep['ws']
+        if stale:                                # replay the forward into the workspace
+            keep = {}
+            with torch.no_grad():
+                _dense_predict_raw(x, y, xs, inv_ls, amp, _keep=keep, **args)
+        n, d, D, ns, batch, pb = keep['dims']
+        L = B.lib()
+        dev = xs.device
+        gm = gc = None
+        if g_mean is not None:
+            gm = _f64c(g_mean).reshape(batch, ns, D)
+        if args['want_cov'] and g_cov is not None:
+            gc = _f64c(g_cov).reshape((batch, ns, ns) if args['full_cov'] else (batch, ns))
+        if gm is None and gc is None:
+            return (None,) * 6
+        g_xs = torch.empty(batch, ns, d, dtype=torch.float64, device=dev)
+        sb = L.ffgp_dense_predict_bwd_scratch_bytes(n, d, ns, batch)
+        scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+        rc = L.ffgp_dense_predict_bwd_f64(B.ptr(keep['xc']), B.ptr(keep['xsc']), B.ptr(keep['ilc']), B.ptr(keep['ac']),
+                                          B.ptr(gm), B.ptr(gc), n, d, D, ns, batch, pb, int(bool(args['full_cov'])),
+                                          B.ptr(keep['ws']), keep['wsb'], B.ptr(g_xs), B.ptr(scratch), sb, B.stream_ptr())
+        B.check(rc, 'ffgp_dense_predict_bwd_f64')
+        keep['used'] = True                      # K*, V in the workspace are consumed: a second backward replays
+        if cache is not None:
+            cache.generation += 1
+        g_xs = g_xs[0] if keep['squeeze'] else g_xs
+        return g_xs.to(ctx.xs_dtype), None, None, None, None, None
 
 
 class FactorCache:
@@ -236,6 +306,7 @@ class FactorCache:
         self.buf = None
         self.key = None
         self.valid = False
+        self.generation = 0          # bumped by every call that writes the workspace (see _PredictDx.backward)
 
     def invalidate(self):
         self.valid = False
@@ -266,8 +337,6 @@ def state_token(module, *tensors):
 class _KernelMatrix(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x1, x2, inv_ls, amp, clamp):
-        if x1.requires_grad or x2.requires_grad:
-            raise NotImplementedError('gradient w.r.t. kernel inputs is not provided by the fused kernel-matrix op')
         out_dtype = x1.dtype
         L = B.lib()
         x1c, x2c = _f64c(x1), _f64c(x2)
@@ -297,7 +366,18 @@ class _KernelMatrix(torch.autograd.Function):
         rc = L.ffgp_kernel_matrix_bwd_f64(B.ptr(x1c), B.ptr(x2c), B.ptr(ilc), B.ptr(ac), B.ptr(gKc), n1, n2, d, 1, 0,
                                           B.ptr(g_il), B.ptr(g_amp), B.ptr(scratch), sb, B.stream_ptr())
         B.check(rc, 'ffgp_kernel_matrix_bwd_f64')
-        return None, None, g_il.reshape(il_shape), g_amp.reshape(amp_shape), None
+        g1 = g2 = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            g1 = torch.empty_like(x1c) if ctx.needs_input_grad[0] else None
+            g2 = torch.empty_like(x2c) if ctx.needs_input_grad[1] else None
+            sb = L.ffgp_kernel_matrix_bwd_x_scratch_bytes(n1, n2, d, 1)
+            scratch = torch.empty(sb, dtype=torch.uint8, device=gK.device)
+            rc = L.ffgp_kernel_matrix_bwd_x_f64(B.ptr(x1c), B.ptr(x2c), B.ptr(ilc), B.ptr(ac), B.ptr(gKc), n1, n2, d, 1, 0,
+                                                B.ptr(g1), B.ptr(g2), B.ptr(scratch), sb, B.stream_ptr())
+            B.check(rc, 'ffgp_kernel_matrix_bwd_x_f64')
+            g1 = g1.to(out_dtype) if g1 is not None else None
+            g2 = g2.to(out_dtype) if g2 is not None else None
+        return g1, g2, g_il.reshape(il_shape), g_amp.reshape(amp_shape), None
 
 
 def kernel_matrix(x1, x2, inv_ls, amp, clamp=False):

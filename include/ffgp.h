@@ -65,6 +65,15 @@ int ffgp_kernel_matrix_bwd_f64(const double* x1, const double* x2, const double*
                                const double* gK, int n1, int n2, int d, int batch, int params_batched,
                                double* g_inv_ls, double* g_amp, void* scratch, size_t scratch_bytes, void* stream);
 
+/* d(sum(gK o K))/d(x1, x2): gradient w.r.t. the INPUT points of the kernel above (either output may be NULL).
+ * Replaces autograd's CdistBackward0/PowBackward0/ExpBackward0 chain of ARDKernel.forward (kernel.py:100-105) and the
+ * MmBackward chain of the two SE kernels when a caller differentiates K w.r.t. its inputs (acquisition optimisers,
+ * DMF_acq.py:226-262).  g_x1 [batch][n1][d], g_x2 [batch][n2][d]. */
+size_t ffgp_kernel_matrix_bwd_x_scratch_bytes(int n1, int n2, int d, int batch);
+int ffgp_kernel_matrix_bwd_x_f64(const double* x1, const double* x2, const double* inv_ls, const double* amp,
+                                 const double* gK, int n1, int n2, int d, int batch, int params_batched,
+                                 double* g_x1, double* g_x2, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Dense GP negative log marginal likelihood (+ analytic gradient), `batch` independent problems.
  *   Sigma = K(x,x) + diag(diag_add) + sigma_add ;  L = chol(Sigma) ;  Gamma = L^-1 y
@@ -115,6 +124,23 @@ int ffgp_dense_predict_f64(const double* x, const double* y, const double* xs,
                            int full_cov, int reuse_factor,
                            void* workspace, size_t workspace_bytes,
                            double* out_mean, double* out_cov, int* info, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Gradient of the posterior w.r.t. the test points:  g_xs = d( <g_mean, mean> + <g_cov, cov> ) / d xs.
+ * Replaces the autograd backward of cigp.forward (cigp_v10.py:24-48) that the acquisition optimisers run per
+ * candidate step (DMF_acq.py:247-254, v1/MF_EI.py:22-31): closed form
+ *   d/dK* = alpha g_mean^T - Sigma^-1 K* (G + G^T)      (diagonal variance: - 2 Sigma^-1 K* diag(g_var))
+ * followed by the input-point gradient of K* (and of K(xs,xs) for the full covariance).
+ * MUST be called with the workspace of the ffgp_dense_predict_f64 call it differentiates (same n, d, D, ns, batch,
+ * out_cov requested when g_cov is given): it reads L^-1, alpha and V from it and overwrites K*, V, Kxx.
+ * g_mean [batch][ns][D] or NULL; g_cov [batch][ns][ns] (full_cov) / [batch][ns] or NULL; g_xs [batch][ns][d].
+ * Kernel mode only (amp != NULL); the hyper-parameters are treated as constants.
+ * --------------------------------------------------------------------------------------- */
+size_t ffgp_dense_predict_bwd_scratch_bytes(int n, int d, int ns, int batch);
+int ffgp_dense_predict_bwd_f64(const double* x, const double* xs, const double* inv_ls, const double* amp,
+                               const double* g_mean, const double* g_cov, int n, int d, int D, int ns, int batch,
+                               int params_batched, int full_cov, void* workspace, size_t workspace_bytes,
+                               double* g_xs, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused fit: NLL (+ gradient) AND the posterior at xs from ONE factorisation per problem - what a BO acquisition

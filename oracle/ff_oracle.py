@@ -342,6 +342,19 @@ def cigp_ard_predict(x, y, xs, length_scales, signal_variance, log_beta):
         return cigp_predict(K, Kx, Kxx, log_beta, y)
 
 
+def cigp_ard_predict_dx(x, y, xs, length_scales, signal_variance, log_beta, w_mean, w_cov):
+    """d( <w_mean, mean> + <w_cov, cov> ) / d xs of cigp.forward by autograd, as the acquisition optimisers obtain
+    it (DMF_acq.py:247-254 differentiate UCB/EI of the posterior w.r.t. the candidate).  Returns (mean, cov, g_xs)."""
+    xs = xs.detach().clone().requires_grad_(True)
+    K = ard_kernel(x, x, length_scales, signal_variance)
+    Kx = ard_kernel(x, xs, length_scales, signal_variance)
+    Kxx = ard_kernel(xs, xs, length_scales, signal_variance)
+    mean, cov = cigp_predict(K, Kx, Kxx, log_beta, y)
+    s = (mean * w_mean).sum() + (cov * w_cov).sum()
+    s.backward()
+    return mean.detach(), cov.detach(), xs.grad
+
+
 def dense_nll_grads_analytic_numpy(x, y, ls_raw, sv_raw, log_beta, eps=1e-9, pi=PI_REF):
     """Independent numpy cross-check (no autograd): closed-form gradient of the cigp NLL
     through Sigma^{-1}.  Used by tests to show the analytic route the CUDA path takes

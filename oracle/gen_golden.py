@@ -348,7 +348,49 @@ def gen_c5():
     save('c5_batch', **out)
 
 
+def gen_predict_dx():
+    """Posterior differentiated w.r.t. the test points through the reference's own cigp.forward (autograd), plus the
+    ARD kernel differentiated w.r.t. both inputs."""
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for tag, N, d, D, Ns in (('a', 150, 5, 2, 9), ('b', 300, 8, 1, 40)):
+        x = torch.rand(N, d, generator=g)
+        y = torch.sin(3 * x @ torch.randn(d, D, generator=g)) + 0.05 * torch.randn(N, D, generator=g)
+        xs = torch.rand(Ns, d, generator=g).requires_grad_(True)
+        ls = torch.exp(torch.rand(d, generator=g) - 0.5)
+        m = cigp(gpk.ARDKernel(d), 2.0)
+        with torch.no_grad():
+            m.kernel.length_scales.copy_(ls)
+            m.kernel.signal_variance.fill_(1.3)
+        wm = torch.randn(Ns, D, generator=g)
+        wc = torch.randn(Ns, Ns, generator=g)
+        mean, cov = m(x, y, xs)
+        ((mean * wm).sum() + (cov * wc).sum()).backward()
+        g_full = xs.grad.clone()
+        xs.grad = None
+        mean, cov = m(x, y, xs)
+        wd = torch.randn(Ns, generator=g)
+        ((mean * wm).sum() + (cov.diag() * wd).sum()).backward()
+        out.update({f'x_{tag}': x, f'y_{tag}': y, f'xs_{tag}': xs, f'ls_{tag}': ls, f'wm_{tag}': wm, f'wc_{tag}': wc,
+                    f'wd_{tag}': wd, f'mean_{tag}': mean, f'cov_{tag}': cov, f'gxs_full_{tag}': g_full,
+                    f'gxs_diag_{tag}': xs.grad})
+    # kernel matrix w.r.t. both inputs
+    x1 = torch.randn(37, 4, generator=g).requires_grad_(True)
+    x2 = torch.randn(29, 4, generator=g).requires_grad_(True)
+    k = gpk.ARDKernel(4)
+    with torch.no_grad():
+        k.length_scales.copy_(torch.tensor([0.7, -1.2, 2.0, 0.9]))
+        k.signal_variance.fill_(0.8)
+    W = torch.randn(37, 29, generator=g)
+    (k(x1, x2) * W).sum().backward()
+    out.update(kx1=x1, kx2=x2, kW=W, k_ls=k.length_scales, k_sv=k.signal_variance, g_kx1=x1.grad, g_kx2=x2.grad)
+    save('predict_dx', **out)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'predict_dx':
+        gen_predict_dx()
+        sys.exit(0)
     gen_kernels()
     gen_kats()
     gen_c2()
@@ -358,3 +400,4 @@ if __name__ == '__main__':
     gen_c4()
     gen_couplings()
     gen_c5()
+    gen_predict_dx()

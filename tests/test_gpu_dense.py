@@ -359,3 +359,86 @@ def test_c2_full_size_anchor_and_gradient_identity():
             p.add_(h)
         fd = (up - dn) / (2 * h)
         assert abs(fd - g0) <= 1e-6 * max(abs(g0), 1.0), (name, fd, g0)
+
+
+def test_kernel_matrix_input_gradients_match_reference_golden():
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
+    g = load_golden('predict_dx')
+    k = ARDKernel(4)
+    with torch.no_grad():
+        k.length_scales.copy_(T(g['k_ls']))
+        k.signal_variance.copy_(T(g['k_sv']))
+    k = k.to(DEV)
+    x1, x2 = G(g['kx1']).requires_grad_(True), G(g['kx2']).requires_grad_(True)
+    (k(x1, x2) * G(g['kW'])).sum().backward()
+    assert rel_err(x1.grad.cpu(), g['g_kx1']) < TOL
+    assert rel_err(x2.grad.cpu(), g['g_kx2']) < TOL
+    # same tensor on both sides (K(x*, x*)): the two contributions add up
+    xx = G(g['kx1']).requires_grad_(True)
+    Wm = torch.randn(37, 37, generator=torch.Generator().manual_seed(0)).to(DEV)
+    (k(xx, xx) * Wm).sum().backward()
+    xo = T(g['kx1']).clone().requires_grad_(True)
+    (O.ard_kernel(xo, xo, T(g['k_ls']), T(g['k_sv'])) * Wm.cpu()).sum().backward()
+    assert rel_err(xx.grad.cpu(), xo.grad) < TOL
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_posterior_gradient_wrt_test_points_matches_reference_golden(tag):
+    """cigp.forward differentiated w.r.t. x_test (acquisition optimisers, DMF_acq.py:247-254): full covariance
+    weights and diagonal-only weights, then a second backward through the same graph (workspace replay)."""
+    g = load_golden('predict_dx')
+    d = g[f'x_{tag}'].shape[1]
+    m = _cigp(d, g[f'ls_{tag}'], 1.3, 2.0)
+    x, y = G(g[f'x_{tag}']), G(g[f'y_{tag}'])
+    xs = G(g[f'xs_{tag}']).requires_grad_(True)
+    mean, cov = m(x, y, xs)
+    assert rel_err(mean.cpu(), g[f'mean_{tag}']) < TOL and rel_err(cov.cpu(), g[f'cov_{tag}']) < TOL
+    s = (mean * G(g[f'wm_{tag}'])).sum() + (cov * G(g[f'wc_{tag}'])).sum()
+    s.backward(retain_graph=True)
+    assert rel_err(xs.grad.cpu(), g[f'gxs_full_{tag}']) < TOL
+    xs.grad = None
+    s.backward()                                   # the workspace was consumed: the forward is replayed
+    assert rel_err(xs.grad.cpu(), g[f'gxs_full_{tag}']) < TOL
+    xs.grad = None
+    mean, cov = m(x, y, xs)                        # factor cache hit
+    ((mean * G(g[f'wm_{tag}'])).sum() + (cov.diagonal() * G(g[f'wd_{tag}'])).sum()).backward()
+    assert rel_err(xs.grad.cpu(), g[f'gxs_diag_{tag}']) < TOL
+    # mean only
+    xs.grad = None
+    mean, _ = m(x, y, xs)
+    (mean * G(g[f'wm_{tag}'])).sum().backward()
+    _, _, gx = O.cigp_ard_predict_dx(T(g[f'x_{tag}']), T(g[f'y_{tag}']), T(g[f'xs_{tag}']), T(g[f'ls_{tag}']), T([1.3]),
+                                     T([2.0]), T(g[f'wm_{tag}']), torch.zeros(xs.shape[0], xs.shape[0]))
+    assert rel_err(xs.grad.cpu(), gx) < TOL
+
+
+def test_posterior_gradient_diag_variance_C_ABI_and_finite_difference():
+    """The diagonal-variance branch of ffgp_dense_predict_bwd_f64 through ops.dense_predict(full_cov=False), checked
+    against the oracle and against a central difference of the CUDA forward itself at N=2048."""
+    from fidelityfusion_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    n, d, ns = 2048, 6, 33
+    x = torch.rand(n, d, generator=gen)
+    y = torch.sin(3 * x.sum(1, keepdim=True)) + 0.05 * torch.randn(n, 1, generator=gen)
+    xs0 = torch.rand(ns, d, generator=gen)
+    il = torch.full((d,), 1 / 0.6)
+    amp, noise = torch.tensor([1.2]), torch.tensor([0.05])
+    wm, wv = torch.randn(ns, 1, generator=gen), torch.randn(ns, generator=gen)
+    cache = ops.FactorCache()
+
+    def f(xs):
+        return ops.dense_predict(x.to(DEV), y.to(DEV), xs, il.to(DEV), amp.to(DEV), diag_add=(noise + 1e-6).to(DEV),
+                                 cov_offset=noise.to(DEV), full_cov=False, cache=cache, cache_token='t')
+
+    xs = xs0.to(DEV).requires_grad_(True)
+    mean, var = f(xs)
+    ((mean * wm.to(DEV)).sum() + (var * wv.to(DEV)).sum()).backward()
+    ls = 0.6 * torch.ones(d) - 1e-9
+    _, _, gx = O.cigp_ard_predict_dx(x, y, xs0, ls, amp, -torch.log(noise), wm, torch.diag(wv))
+    assert rel_err(xs.grad.cpu(), gx) < 1e-8       # cond(Sigma) ~ 1e5 at this size; the oracle's own autograd noise
+    with torch.no_grad():
+        h = 1e-5
+        e = torch.zeros(ns, d); e[3, 2] = h
+        s = lambda o: float(((o[0] * wm.to(DEV)).sum() + (o[1] * wv.to(DEV)).sum()).item())
+        fd = (s(f((xs0 + e).to(DEV))) - s(f((xs0 - e).to(DEV)))) / (2 * h)
+    assert abs(fd - xs.grad[3, 2].item()) < 1e-5 * max(1.0, abs(fd))

@@ -274,3 +274,18 @@ def test_c5_batch():
         assert rel_err(gr['log_beta'], g[f'g_lb{b}']) < 1e-10
         mean, cov = O.cigp_ard_predict(x, y, xs, T(g[f'ls{b}']), T([1.0]), T([float(g[f'lb{b}'])]))
         assert rel_err(mean, g[f'mean{b}']) < TOL and rel_err(cov.diag(), g[f'vdiag{b}']) < TOL
+
+
+def test_posterior_gradient_wrt_test_points():
+    """d posterior / d x* and d K / d inputs: oracle (autograd restatement) vs the reference's own autograd."""
+    g = load_golden('predict_dx')
+    for tag in ('a', 'b'):
+        x, y, xs, ls = T(g[f'x_{tag}']), T(g[f'y_{tag}']), T(g[f'xs_{tag}']), T(g[f'ls_{tag}'])
+        mean, cov, gx = O.cigp_ard_predict_dx(x, y, xs, ls, T([1.3]), T([2.0]), T(g[f'wm_{tag}']), T(g[f'wc_{tag}']))
+        assert rel_err(mean, g[f'mean_{tag}']) < TOL and rel_err(cov, g[f'cov_{tag}']) < 1e-11
+        assert rel_err(gx, g[f'gxs_full_{tag}']) < 1e-10
+        _, _, gx = O.cigp_ard_predict_dx(x, y, xs, ls, T([1.3]), T([2.0]), T(g[f'wm_{tag}']), torch.diag(T(g[f'wd_{tag}'])))
+        assert rel_err(gx, g[f'gxs_diag_{tag}']) < 1e-10
+    x1, x2 = P(g['kx1']), P(g['kx2'])
+    (O.ard_kernel(x1, x2, T(g['k_ls']), T(g['k_sv'])) * T(g['kW'])).sum().backward()
+    assert rel_err(x1.grad, g['g_kx1']) < 1e-11 and rel_err(x2.grad, g['g_kx2']) < 1e-11
