@@ -49,6 +49,7 @@ def lib():
     _sig(L.ffgp_kernel_matrix_bwd_x_f64, i, [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp])
     _sig(L.ffgp_dense_predict_bwd_scratch_bytes, sz, [i, i, i, i])
     _sig(L.ffgp_dense_predict_bwd_f64, i, [vp] * 6 + [i] * 7 + [vp, sz, vp, vp, sz, vp])
+    _sig(L.ffgp_acquisition_f64, i, [vp, vp, i, i, ctypes.c_double, ctypes.c_double, ctypes.c_double, i, vp, vp, vp, vp])
     _sig(L.ffgp_dense_workspace_bytes, sz, [i, i, i, i, i])
     _sig(L.ffgp_dense_nll_f64, i, [vp] * 6 + [i] * 7 + [vp, sz] + [vp] * 7 + [vp, vp])
     _sig(L.ffgp_dense_predict_f64, i, [vp] * 10 + [i] * 9 + [vp, sz] + [vp, vp, vp, vp])

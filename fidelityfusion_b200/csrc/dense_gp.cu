@@ -10,6 +10,7 @@
 #include "gemm_dmma.cuh"
 #include "gemm_tma.cuh"
 #include "xgrad_kernels.cuh"
+#include "acq_kernels.cuh"
 
 namespace ffgp {
 
@@ -342,8 +343,16 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
     const int rows1 = np - (k + 1) * NB;            // rows below block row k
     // (a) rank-NB update of block column k+1
     g_trace_label = "a:colupd";
-    if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1), c.ld,
-                  c.sb, rows1, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+    if (!lookahead) {
+      // batched problems (no panel chain to protect): the NB x NB diagonal block of the column is symmetric - lower
+      // tiles only, and only the lower fragments of its diagonal tiles - then the rectangle below it
+      if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1), c.ld,
+                    c.sb, NB, NB, NB, -1.0, 1.0, 1, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+      if (rows1 > NB &&
+          (e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 2, k + 1), c.ld,
+                    c.sb, rows1 - NB, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+    } else if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1),
+                         c.ld, c.sb, rows1, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
     cudaStream_t ps = c.st;
     if (aux) {
       if ((e = cudaEventRecord(aux->ev_main, c.st)) != cudaSuccess) return e;
@@ -951,6 +960,19 @@ int ffgp_dense_predict_bwd_f64(const double* x, const double* xs, const double* 
     q.gK = w.Kxx; q.ldr = w.nsp; q.ldc = 1; q.sgK = sKxx; q.gk_scale = 1.0;
     if ((rc = launch_xgrad(q, batch, g_xs, 1, st)) != 0) return rc;
   }
+  return 0;
+}
+
+int ffgp_acquisition_f64(const double* mean, const double* var, int m, int kind, double f_best, double beta, double xi,
+                         int round_f32, double* score, double* d_mean, double* d_var, void* stream) {
+  if (!mean || !var || !score) return fail(-1, "ffgp_acquisition_f64: null pointer");
+  if (m <= 0 || kind < 0 || kind > 2) return fail(-2, "ffgp_acquisition_f64: bad size or kind (0 UCB, 1 EI, 2 PI)");
+  AcqParams p;
+  p.mean = mean; p.var = var; p.m = m; p.kind = kind; p.f_best = f_best; p.beta = beta; p.xi = xi;
+  p.std_min = 1e-9; p.two_pi = 2.0 * 3.1415926;          /* DMF_acq.py:7,98,121 */
+  p.round_f32 = round_f32; p.score = score; p.d_mean = d_mean; p.d_var = d_var;
+  acq_kernel<<<(m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  FFGP_LAUNCHED();
   return 0;
 }
 

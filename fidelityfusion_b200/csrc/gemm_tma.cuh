@@ -84,6 +84,15 @@ __device__ __forceinline__ double tg_lds(uint32_t addr) {
   return v;
 }
 
+// Compile-time set of live 8x8 accumulator fragments of a consumer warp in one k-step (see the kernel):
+// i in [ILO, IHI), j in [JLO, JHI), and for ROLE = 4 wm + wn >= 0 only fragments on/below the tile diagonal.
+template <int ILO, int IHI, int JLO, int JHI, int ROLE>
+struct TgLive {
+  __device__ static constexpr bool live(int i, int j) {
+    return i >= ILO && i < IHI && j >= JLO && j < JHI && (ROLE < 0 || 2 * i + (ROLE >> 2) - 4 * j - (ROLE & 3) >= 0);
+  }
+};
+
 // A_KMAJ: A(i,p) = A[i*lda + p]  else  A(i,p) = A[p*lda + i];   B_KMAJ: B(p,j) = B[j*ldb + p]  else  B[p*ldb + j]
 template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(TG_THREADS, 1)
@@ -151,9 +160,26 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   // ===================== DMMA consumers =====================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TG_REGS_CONSUMER));
-  const int wm = warp >> 2, wn = warp & 3;                 // 2 x 4 warps, warp tile 64 x 32
+  // 2 x 4 warps, warp tile 64 x 32 made of CYCLICALLY assigned 8-wide fragments: m-fragment i of warp row wm covers tile
+  // rows (2 i + wm) * 8 .., n-fragment j of warp column wn covers tile columns (4 j + wn) * 8 ..  Every warp then owns
+  // the same share of any triangular region of the tile, so structural zeros (below) can be skipped without one warp
+  // becoming the straggler.  Warps w and w + 4 share an SM sub-partition: wn is mirrored in the second warp row so the
+  // sub-partitions' DMMA counts on a symmetric diagonal tile are 36/32/36/32 of 64.
+  const int wm = warp >> 2, wn = (warp & 3) ^ (wm ? 3 : 0);
   const int g = lane >> 2, tq = lane & 3;
   constexpr int MT = 8, NT = 4;
+  // ---- structural zeros.  A kmode says an operand is TRIANGULAR (ffgp.h): besides shortening the K range of the tile,
+  // inside the one 128-deep K block that straddles the diagonal a k4 step only touches fragments whose rows (columns)
+  // reach it; and a lower_only diagonal tile is symmetric, only fragments on/below its diagonal are produced (the rest
+  // of the tile is left untouched).  At N = 512 (BASELINE config 5) this removes 1/3 of the DMMAs of a factorisation.
+  const bool sym_diag = p.lower_only && ti == tj;
+  int tri_kt0 = -1;                                        // first k-step (of 8) of the diagonal K block, -1: none
+  int tri_mode = 0;                                        // 1: A rows >= p   2: B cols >= p   3: B cols <= p   4: A rows <= p
+  if (p.kmode == K_LE_ROW && k_hi == i0 + TG_BM) { tri_mode = 1; tri_kt0 = KT - TG_BM / TG_BK; }
+  else if (p.kmode == K_LE_COL && k_hi == j0 + TG_BN) { tri_mode = 2; tri_kt0 = KT - TG_BN / TG_BK; }
+  else if (p.kmode == K_GE_COL) { tri_mode = 3; tri_kt0 = 0; }
+  else if (p.kmode == K_GE_ROW) { tri_mode = 4; tri_kt0 = 0; }
+  const int sym_thr = sym_diag ? 0 : -64;                 // fragment (i, j) is produced iff 2 i + wm - 4 j - wn >= sym_thr
   double* __restrict__ Cg = p.C + (long long)zo * p.sC + (long long)zi * p.iC;
   const double alpha = p.alpha, beta = p.beta;
 
@@ -164,11 +190,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const double r = beta / alpha;
 #pragma unroll
     for (int i = 0; i < MT; i++) {
-      const int row = i0 + wm * 64 + i * 8 + g;
+      const int row = i0 + (2 * i + wm) * 8 + g;
 #pragma unroll
       for (int j = 0; j < NT; j++) {
-        const int col = j0 + wn * 32 + j * 8 + tq * 2;
-        const double2 o = *reinterpret_cast<const double2*>(Cg + (long long)row * p.ldc + col);
+        const int col = j0 + (4 * j + wn) * 8 + tq * 2;
+        double2 o = make_double2(0.0, 0.0);
+        if (2 * i + wm - 4 * j - wn >= sym_thr) o = *reinterpret_cast<const double2*>(Cg + (long long)row * p.ldc + col);
         acc[i][j][0] = r * o.x;
         acc[i][j][1] = r * o.y;
       }
@@ -182,26 +209,30 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   // per-thread fragment offsets inside a stage (bytes)
   const uint32_t swz_h = (uint32_t)((tq >> 1) ^ g);        // k-major: 16-B chunk index = (2 kk + (tq>>1)) ^ (row & 7)
-  const uint32_t a_off = A_KMAJ ? (uint32_t)((wm * 64 + g) * 128 + ((tq & 1) << 3))
-                                : (uint32_t)(wm * 8 * 1024 + tq * 64 + g * 8);
-  const uint32_t b_off = TG_PANEL_BYTES + (B_KMAJ ? (uint32_t)((wn * 32 + g) * 128 + ((tq & 1) << 3))
-                                                  : (uint32_t)(wn * 4 * 1024 + tq * 64 + g * 8));
+  const uint32_t a_off = A_KMAJ ? (uint32_t)((wm * 8 + g) * 128 + ((tq & 1) << 3))
+                                : (uint32_t)(wm * 1024 + tq * 64 + g * 8);
+  const uint32_t b_off = TG_PANEL_BYTES + (B_KMAJ ? (uint32_t)((wn * 8 + g) * 128 + ((tq & 1) << 3))
+                                                  : (uint32_t)(wn * 1024 + tq * 64 + g * 8));
   double af[2][MT], bf[2][NT];
   auto load_frags = [&](int buf, uint32_t stage_base, int kk) {
     const uint32_t kx = A_KMAJ || B_KMAJ ? (((uint32_t)(2 * kk) ^ swz_h) << 4) : 0u;
     const uint32_t pa = stage_base + a_off + (A_KMAJ ? kx : (uint32_t)(kk * 256));
     const uint32_t pb = stage_base + b_off + (B_KMAJ ? kx : (uint32_t)(kk * 256));
 #pragma unroll
-    for (int i = 0; i < MT; i++) af[buf][i] = tg_lds(pa + i * 1024);
+    for (int i = 0; i < MT; i++) af[buf][i] = tg_lds(pa + i * 2048);
 #pragma unroll
-    for (int j = 0; j < NT; j++) bf[buf][j] = tg_lds(pb + j * 1024);
+    for (int j = 0; j < NT; j++) bf[buf][j] = tg_lds(pb + j * 4096);
   };
 
   if (KT > 0) {
     tg_mbar_wait(bar_base, 0);
     load_frags(0, smem_base, 0);
   }
-  for (int kt = 0; kt < KT; kt++) {
+  // One k-step (16 deep = 4 k4 steps) with the compile-time set of live fragments `Lv`: straight-line DMMAs, no
+  // per-instruction predicates (a first version predicated every DMMA: the compiler guards each with WARPSYNC + a
+  // chain of ISETPs and the "skipped" work cost more than doing it, profiles/r01_c5_trisk_v1.txt).
+  auto kt_body = [&](auto lv, int kt) {
+    using Lv = decltype(lv);
     const int s = kt % TG_STAGES;
     const uint32_t stage_base = smem_base + s * TG_STAGE_BYTES;
 #pragma unroll
@@ -217,22 +248,79 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < MT; i++)
 #pragma unroll
-        for (int j = 0; j < NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        for (int j = 0; j < NT; j++)
+          if (Lv::live(i, j)) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
       if (kk == TG_BK / 4 - 2) {
         // the last fragments of this stage are in registers: hand the stage back to the producer
         __syncwarp();
         if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s);
       }
     }
+  };
+  const int role = wm * 4 + wn;
+  for (int kt = 0; kt < KT; kt++) {
+    // variant of this k-step (warp-uniform): 0 dense | 1..7 i >= v | 8..14 i < v-7 | 15..17 j >= v-14 | 18..20 j < v-17 |
+    // 21..28 symmetric diagonal tile, by warp role.  Ranges are the union over the four k4 steps of the k-step.
+    int variant = 0;
+    if (sym_diag) {
+      variant = 21 + role;
+    } else if (tri_mode != 0 && kt >= tri_kt0 && kt < tri_kt0 + TG_BM / TG_BK) {
+      const int pk = (kt - tri_kt0) * TG_BK;             // first k of the step inside the diagonal K block
+      if (tri_mode == 1) {                               // (2 i + wm) * 8 + 7 >= pk
+        const int lo = min(MT - 1, (pk - 7 - 8 * wm + 15) >> 4);
+        if (lo > 0) variant = lo;
+      } else if (tri_mode == 4) {                        // (2 i + wm) * 8 <= pk + 15
+        const int hi = max(1, ((pk + 15 - 8 * wm) >> 4) + 1);
+        if (hi < MT) variant = 7 + hi;
+      } else if (tri_mode == 2) {                        // (4 j + wn) * 8 + 7 >= pk
+        const int lo = min(NT - 1, (pk - 7 - 8 * wn + 31) >> 5);
+        if (lo > 0) variant = 14 + lo;
+      } else {                                           // (4 j + wn) * 8 <= pk + 15
+        const int hi = max(1, ((pk + 15 - 8 * wn) >> 5) + 1);
+        if (hi < NT) variant = 17 + hi;
+      }
+    }
+    switch (variant) {
+      case 0: kt_body(TgLive<0, MT, 0, NT, -1>{}, kt); break;
+      case 1: kt_body(TgLive<1, MT, 0, NT, -1>{}, kt); break;
+      case 2: kt_body(TgLive<2, MT, 0, NT, -1>{}, kt); break;
+      case 3: kt_body(TgLive<3, MT, 0, NT, -1>{}, kt); break;
+      case 4: kt_body(TgLive<4, MT, 0, NT, -1>{}, kt); break;
+      case 5: kt_body(TgLive<5, MT, 0, NT, -1>{}, kt); break;
+      case 6: kt_body(TgLive<6, MT, 0, NT, -1>{}, kt); break;
+      case 7: kt_body(TgLive<7, MT, 0, NT, -1>{}, kt); break;
+      case 8: kt_body(TgLive<0, 1, 0, NT, -1>{}, kt); break;
+      case 9: kt_body(TgLive<0, 2, 0, NT, -1>{}, kt); break;
+      case 10: kt_body(TgLive<0, 3, 0, NT, -1>{}, kt); break;
+      case 11: kt_body(TgLive<0, 4, 0, NT, -1>{}, kt); break;
+      case 12: kt_body(TgLive<0, 5, 0, NT, -1>{}, kt); break;
+      case 13: kt_body(TgLive<0, 6, 0, NT, -1>{}, kt); break;
+      case 14: kt_body(TgLive<0, 7, 0, NT, -1>{}, kt); break;
+      case 15: kt_body(TgLive<0, MT, 1, NT, -1>{}, kt); break;
+      case 16: kt_body(TgLive<0, MT, 2, NT, -1>{}, kt); break;
+      case 17: kt_body(TgLive<0, MT, 3, NT, -1>{}, kt); break;
+      case 18: kt_body(TgLive<0, MT, 0, 1, -1>{}, kt); break;
+      case 19: kt_body(TgLive<0, MT, 0, 2, -1>{}, kt); break;
+      case 20: kt_body(TgLive<0, MT, 0, 3, -1>{}, kt); break;
+      case 21: kt_body(TgLive<0, MT, 0, NT, 0>{}, kt); break;
+      case 22: kt_body(TgLive<0, MT, 0, NT, 1>{}, kt); break;
+      case 23: kt_body(TgLive<0, MT, 0, NT, 2>{}, kt); break;
+      case 24: kt_body(TgLive<0, MT, 0, NT, 3>{}, kt); break;
+      case 25: kt_body(TgLive<0, MT, 0, NT, 4>{}, kt); break;
+      case 26: kt_body(TgLive<0, MT, 0, NT, 5>{}, kt); break;
+      case 27: kt_body(TgLive<0, MT, 0, NT, 6>{}, kt); break;
+      default: kt_body(TgLive<0, MT, 0, NT, 7>{}, kt); break;
+    }
   }
 
   // ---- epilogue: C fragment (row g, cols 2 tq, 2 tq + 1) -> 16-byte stores ----------------------
 #pragma unroll
   for (int i = 0; i < MT; i++) {
-    const int row = i0 + wm * 64 + i * 8 + g;
+    const int row = i0 + (2 * i + wm) * 8 + g;
 #pragma unroll
     for (int j = 0; j < NT; j++) {
-      const int col = j0 + wn * 32 + j * 8 + tq * 2;
+      if (2 * i + wm - 4 * j - wn < sym_thr) continue;      // above the diagonal of a symmetric tile: not produced
+      const int col = j0 + (4 * j + wn) * 8 + tq * 2;
       double2* dst = reinterpret_cast<double2*>(Cg + (long long)row * p.ldc + col);
       double2 v;
       if (init_from_c || beta == 0.0) {

@@ -143,6 +143,19 @@ int ffgp_dense_predict_bwd_f64(const double* x, const double* xs, const double* 
                                double* g_xs, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Acquisition scores of m candidates from their posterior mean / variance, with the partial derivatives
+ * d score / d mean and d score / d var (either may be NULL) in the same pass - chained with
+ * ffgp_dense_predict_bwd_f64 this is the whole candidate-optimisation step on the device.
+ * Replaces DiscreteAcquisitionFunction.UCB_MF / EI_MF / PI_MF (MF_BayesianOptimization/Discrete/DMF_acq.py:47-128),
+ * whose EI goes through scipy.stats.norm on the host (DMF_acq.py:104).
+ *   kind 0: mean + beta * var            kind 1: t Phi(z) + s phi(z), t = mean - f_best - xi, s = max(sqrt(var), 1e-9), z = t / s
+ *   kind 2: -z^2/2 - log sqrt(2 * 3.1415926)
+ * round_f32 != 0 (EI): Phi and phi are rounded to float32 as the reference's torch.tensor(norm.cdf(..), dtype=float32).
+ * --------------------------------------------------------------------------------------- */
+int ffgp_acquisition_f64(const double* mean, const double* var, int m, int kind, double f_best, double beta, double xi,
+                         int round_f32, double* score, double* d_mean, double* d_var, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused fit: NLL (+ gradient) AND the posterior at xs from ONE factorisation per problem - what a BO acquisition
  * sweep needs per candidate (train step, then predict: v1/CFKG.py:124-129 re-trains and predicts per candidate).
  * Same arguments as ffgp_dense_nll_f64 + ffgp_dense_predict_f64; out_mean == NULL skips the prediction,

@@ -355,6 +355,22 @@ def cigp_ard_predict_dx(x, y, xs, length_scales, signal_variance, log_beta, w_me
     return mean.detach(), cov.detach(), xs.grad
 
 
+def acq_score(mean, var, kind, f_best=0.0, x_dimension=5):
+    """DiscreteAcquisitionFunction.UCB_MF / EI_MF / PI_MF (MF_BayesianOptimization/Discrete/DMF_acq.py:47-128), with the
+    reference's host round trip through scipy.stats.norm and its float32 rounding of cdf/pdf (DMF_acq.py:104)."""
+    from scipy.stats import norm
+    PI_ACQ = 3.1415926                                         # DMF_acq.py:7
+    if kind == 'UCB':
+        return mean + 0.2 * int(x_dimension) * var
+    std = torch.clamp(torch.sqrt(var), min=1e-9)
+    Z = (mean - f_best - 0.01) / std
+    if kind == 'EI':
+        cdf = torch.tensor(norm.cdf(Z.detach().numpy()), dtype=torch.float32)
+        pdf = torch.tensor(norm.pdf(Z.detach().numpy()), dtype=torch.float32)
+        return (mean - f_best - 0.01) * cdf + std * pdf
+    return -torch.pow(Z, 2) * 0.5 - torch.log(torch.ones(1, 1)) - torch.log(torch.sqrt(2 * PI_ACQ * torch.ones(1, 1)))
+
+
 def dense_nll_grads_analytic_numpy(x, y, ls_raw, sv_raw, log_beta, eps=1e-9, pi=PI_REF):
     """Independent numpy cross-check (no autograd): closed-form gradient of the cigp NLL
     through Sigma^{-1}.  Used by tests to show the analytic route the CUDA path takes
