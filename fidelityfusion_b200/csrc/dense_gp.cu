@@ -75,6 +75,17 @@ static bool use_tma_gemm() {
 }
 
 static thread_local int g_cta_cap = 0;   // > 0: see gemm()
+// Batched small problems (no priority chain to protect): the TMA GEMM runs as a persistent grid, see launch_gemm_tma.
+// Measured per launch at 512 x (N = 512) (profiles/r01_launches_c5_v7_persistent.txt): 5-9 % faster for the products
+// with beta = 0, but slower where the epilogue has to read C (SYRK updates: +25 %) and for the lower-tiles-only
+// M^T M product (+20 %), so only the former use it.
+// FFGP_PERSIST=0 disables it (A/B comparisons), FFGP_PERSIST=2 forces it for every launch (tests/test_gpu_gemm.py).
+static thread_local int g_persist = 0;
+static int persist_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_PERSIST"); v = e ? atoi(e) : 1; }
+  return v;
+}
 static thread_local const char* g_trace_label = "gemm";
 
 static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long long sA, const double* B, int ldb,
@@ -128,7 +139,7 @@ static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long
     if (tiles < (long long)num_sms()) big = false;     // 64x64 tiles: 4x the CTAs for the small levels
   }
   cudaError_t e = cudaErrorNotSupported;
-  if (big && use_tma_gemm()) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st);
+  if (big && use_tma_gemm()) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st, (persist_mode() == 2 || (g_persist && persist_mode() == 1 && beta == 0.0 && !lower_only)) ? num_sms() : 0);
   if (e == cudaErrorNotSupported) {
     if (a_kmaj && b_kmaj) e = launch_gemm<true, true>(p, batch, big, st);
     else if (a_kmaj && !b_kmaj) e = launch_gemm<true, false>(p, batch, big, st);
@@ -514,14 +525,16 @@ static cudaError_t ensure_attrs() {
   if (g_attr_done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(potrf_trtri_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem_doubles(GRAD_DMAX) * 8);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   g_attr_done = true;
   return cudaSuccess;
 }
 
 static size_t grad_smem_bytes(int d) {
-  return (size_t)(2 * GRAD_T * (d + 1) + 2 * GRAD_T * 8 + 8 * (GRAD_DMAX + 1)) * sizeof(double);
+  return grad_smem_doubles(d) * sizeof(double);
 }
 
 struct DenseArgs {
@@ -689,8 +702,10 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
   DenseArgs a{x, y, inv_ls, amp, diag_add, sigma_add, n, d, D, batch, params_batched, /*diag_batched=*/params_batched, clamp};
   if (!reuse_factor) FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
   const long long sM = (long long)w.np * w.np;
+  struct PersistGuard { ~PersistGuard() { g_persist = 0; } } persist_guard;
   for (int b0 = 0; b0 < batch; b0 += w.chunk) {
     const int nb = std::min(w.chunk, batch - b0);
+    g_persist = nb >= 8;      // same rule as the look-ahead switch: a large batch fills the machine by itself
     int rc;
     if (!reuse_factor) {
       if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;

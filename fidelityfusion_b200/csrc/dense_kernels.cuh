@@ -636,6 +636,24 @@ struct GradParams {
   int have_k;                                     // 0: no kernel part (covariance-input mode)
 };
 
+// Shared-memory plan of grad_contract_kernel for input dimension d (doubles).  The scaled inputs of the tile's rows
+// and columns are held with the dimension count padded to whole 8-wide MMA fragments.
+__host__ __device__ inline int grad_nz(int d) { return (d + 7) / 8; }               // 8-wide fragments over the dimensions
+__host__ __device__ inline int grad_ldz(int d) { return grad_nz(d) * 8 + 4; }       // row stride of zi / zj (conflict-free fragments)
+constexpr int GRAD_LDW = GRAD_T + 4;
+__host__ __device__ inline size_t grad_smem_doubles(int d) {
+  return (size_t)2 * GRAD_T * grad_ldz(d) + (size_t)GRAD_T * GRAD_LDW + 2 * GRAD_T * 8 + 8 * GRAD_T + 8 * (GRAD_DMAX + 1);
+}
+
+// Formulation (everything level-3 on the FP64 tensor pipe, the elementwise part is one exp per pair):
+//   z = (x - x_0) o w   (the kernel is translation invariant; centring on the problem's first point keeps the
+//                        norm expansions below well conditioned when the inputs carry a large offset)
+//   sq_ij = |z_i|^2 + |z_j|^2 - 2 (Zi Zj^T)_ij                      cross term: DMMA, k = d
+//   W_ij  = G_ij exp(-sq_ij / 2)   (x2 below the diagonal: the mirrored pair; diagonal: G_ii)
+//   sum_ij W_ij (z_ik - z_jk)^2 = sum_i R_i z_ik^2 + sum_j C_j z_jk^2 - 2 sum_i z_ik (W Zj)_ik     W Zj: DMMA, k = 64
+// with R / C the row / column sums of the tile's W.  The previous version evaluated (z_ik - z_jk)^2 pair by pair and
+// dimension by dimension twice (5 d + 45 FP64 instructions per pair, FP64-FMA bound: 0.88 ms per 512 problems of
+// N = 512, d = 8, profiles/r01_launches_c5_v6.csv); this one needs about 35 per pair independent of d.
 __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) {
   extern __shared__ __align__(16) double gsm[];
   const int b = blockIdx.y;
@@ -645,21 +663,43 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
   while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
   const int tj = t - ti * (ti + 1) / 2;
   const int i0 = ti * GRAD_T, j0 = tj * GRAD_T;
-  const int d = p.d, ldx = d + 1;
-  double* xi = gsm;                         // [64][d+1]
-  double* xj = xi + GRAD_T * ldx;           // [64][d+1]
-  double* ai = xj + GRAD_T * ldx;           // [64][8]
+  const int d = p.have_k ? p.d : 0;
+  const int nz = grad_nz(d), ldz = grad_ldz(p.d), dz = nz * 8;       // dz: dimensions padded with zeros
+  double* zi = gsm;                         // [64][ldz]
+  double* zj = zi + GRAD_T * ldz;           // [64][ldz]
+  double* Wsm = zj + GRAD_T * ldz;          // [64][GRAD_LDW]
+  double* ai = Wsm + GRAD_T * GRAD_LDW;     // [64][8]
   double* aj = ai + GRAD_T * 8;             // [64][8]
-  double* red = aj + GRAD_T * 8;            // [8 warps][GRAD_DMAX + 1]
-  const int tid = threadIdx.x;
+  double* nrm = aj + GRAD_T * 8;            // [2][64] squared norms of the rows of zi, zj
+  double* rowp = nrm + 2 * GRAD_T;          // [4 warp columns][64] partial row sums of W
+  double* colp = rowp + 4 * GRAD_T;         // [2 warp rows][64] partial column sums of W
+  double* red = colp + 2 * GRAD_T;          // [8 warps][GRAD_DMAX + 1]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
   const double* x = p.x ? p.x + b * p.sx : nullptr;
   const double* w = p.w ? p.w + b * p.sw : nullptr;
-  if (p.have_k) {
-    for (int e = tid; e < 2 * GRAD_T * d; e += 256) {
-      const int which = e / (GRAD_T * d), r = (e / d) % GRAD_T, k = e % d;
+  const int wm = warp >> 2, wn = warp & 3;           // 2 x 4 warps, warp tile 32 x 16
+  // the thread's 16 entries of S (or G), requested before anything else: their latency hides behind the z staging
+  double2 sreg[4][2];
+  {
+    const double* src = p.src + b * p.ssrc;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int gi = i0 + wm * 32 + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int gc = j0 + wn * 16 + j * 8 + tq * 2;
+        sreg[i][j] = (gi < p.n && gc <= gi) ? *reinterpret_cast<const double2*>(src + (long long)gi * p.ld + gc)
+                                           : make_double2(0.0, 0.0);
+      }
+    }
+  }
+  if (d > 0) {
+    for (int e = tid; e < 2 * GRAD_T * dz; e += 256) {
+      const int which = e / (GRAD_T * dz), r = (e / dz) % GRAD_T, k = e % dz;
       const int gi = (which ? j0 : i0) + r;
-      const double v = (gi < p.n) ? x[(long long)gi * d + k] * w[k] : 0.0;
-      (which ? xj : xi)[r * ldx + k] = v;
+      const double v = (gi < p.n && k < d) ? (x[(long long)gi * d + k] - x[k]) * w[k] : 0.0;
+      (which ? zj : zi)[r * ldz + k] = v;
     }
   }
   if (!p.src_is_G) {
@@ -671,80 +711,128 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
     }
   }
   __syncthreads();
-  // thread -> 4x4 micro tile: rows r0..r0+3 (stride 16 apart keeps smem reads conflict-light)
-  const int tr = tid >> 4, tc = tid & 15;
+  if (tid < 2 * GRAD_T) {
+    const double* zr = (tid < GRAD_T ? zi : zj) + (tid % GRAD_T) * ldz;
+    double s = 0.0;
+    for (int k = 0; k < dz; k++) s = fma(zr[k], zr[k], s);
+    nrm[tid] = s;
+  }
+  // ---- cross term Zi Zj^T ----
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  for (int kk = 0; kk < dz; kk += 4) {
+    double af[4], bf[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) af[i] = zi[(wm * 32 + i * 8 + g) * ldz + kk + tq];
+#pragma unroll
+    for (int j = 0; j < 2; j++) bf[j] = zj[(wn * 16 + j * 8 + g) * ldz + kk + tq];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+  __syncthreads();                                   // norms
+  // ---- W = G o K/amp on the thread's 16 pairs (C-fragment layout: row g, columns 2 tq, 2 tq + 1) ----
+  // Straight-line over the 16 pairs (select, no branches): the 16 exp() polynomial chains interleave.  A branchy
+  // version left the FP64 pipe 14 % busy, stalled on the dependent chain of one exp at a time
+  // (profiles/r01_ncu_grad_contract_v2.txt).
   const double amp = p.have_k ? p.amp[b * p.samp] : 0.0;
-  const double* src = p.src + b * p.ssrc;
-  double Wv[4][4];
-  double sumW = 0.0;
-  // pass 1: squared distances of the 4x4 pairs, operands loaded once per input dimension
-  double sq[4][4];
+  double wv[4][2][2];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int i = 0; i < 4; i++) {
+    const int r = wm * 32 + i * 8 + g;
 #pragma unroll
-    for (int q = 0; q < 4; q++) sq[a][q] = 0.0;
-  if (p.have_k) {
-    for (int k = 0; k < d; k++) {
-      double xr[4], xc[4];
+    for (int j = 0; j < 2; j++) {
+      const int c0 = wn * 16 + j * 8 + tq * 2;
 #pragma unroll
-      for (int a = 0; a < 4; a++) xr[a] = xi[(tr + 16 * a) * ldx + k];
-#pragma unroll
-      for (int q = 0; q < 4; q++) xc[q] = xj[(tc + 16 * q) * ldx + k];
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int q = 0; q < 4; q++) { const double dz = xr[a] - xc[q]; sq[a][q] = fma(dz, dz, sq[a][q]); }
+      for (int e = 0; e < 2; e++) {
+        const double sq = fmax(nrm[r] + nrm[GRAD_T + c0 + e] - 2.0 * acc[i][j][e], 0.0);
+        wv[i][j][e] = exp(-0.5 * sq);
+      }
     }
   }
+  double sumW = 0.0;
+  double rsum[4] = {0.0, 0.0, 0.0, 0.0}, csum[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-  for (int a = 0; a < 4; a++) {
-    const int r = tr + 16 * a, gi = i0 + r;
+  for (int i = 0; i < 4; i++) {
+    const int r = wm * 32 + i * 8 + g, gi = i0 + r;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int c = tc + 16 * q, gj = j0 + c;
-      double wgt = 0.0;
-      if (gi < p.n && gj < p.n && gj <= gi) {
-        double G = src[(long long)gi * p.ld + gj];
+    for (int j = 0; j < 2; j++) {
+      const int c0 = wn * 16 + j * 8 + tq * 2;
+      const double sv[2] = {sreg[i][j].x, sreg[i][j].y};
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = c0 + e, gj = j0 + c;
+        const bool valid = gi < p.n && gj <= gi;
+        double G = sv[e];
         if (!p.src_is_G) {
           double aa = 0.0;
-#pragma unroll
-          for (int cc = 0; cc < 8; cc++) aa = fma(ai[r * 8 + cc], aj[c * 8 + cc], aa);
+          for (int cc = 0; cc < p.D; cc++) aa = fma(ai[r * 8 + cc], aj[c * 8 + cc], aa);
           G = 0.5 * ((double)p.D * G - aa);
         }
-        if (p.G_out) {
+        if (valid && p.G_out) {
           double* go = p.G_out + b * p.sGo;
           go[(long long)gi * p.n + gj] = G;
           go[(long long)gj * p.n + gi] = G;
         }
-        if (gi == gj) {
-          if (p.g_diag) p.g_diag[b * p.sgd + gi] = G;
-          wgt = G;                             // K_ii / amp = 1, dz = 0
-        } else if (p.have_k) {
-          wgt = 2.0 * G * exp(-0.5 * sq[a][q]);   // (i,j) and (j,i); amplitude applied below
-        }
+        if (valid && gi == gj && p.g_diag) p.g_diag[b * p.sgd + gi] = G;
+        // diagonal: K_ii / amp = 1, dz = 0; below it the pair stands for (i,j) and (j,i); amplitude applied at the end
+        const double wgt = !valid ? 0.0 : (gi == gj ? G : (p.have_k ? 2.0 * G * wv[i][j][e] : 0.0));
+        wv[i][j][e] = wgt;
       }
-      sumW += wgt;                             // sum G o (K / amp): d/d amp needs no division (amp may be 0)
-      Wv[a][q] = wgt * amp;
+      sumW += wv[i][j][0] + wv[i][j][1];             // sum G o (K / amp): d/d amp needs no division (amp may be 0)
+      rsum[i] += wv[i][j][0] + wv[i][j][1];
+      csum[j][0] += wv[i][j][0];
+      csum[j][1] += wv[i][j][1];
+      *reinterpret_cast<double2*>(Wsm + r * GRAD_LDW + c0) = make_double2(wv[i][j][0], wv[i][j][1]);
     }
   }
-  const int warp = tid >> 5, lane = tid & 31;
-  double* part = p.partial + ((long long)b * p.npart + t) * (d + 1);
-  if (p.have_k) {
-    // pass 2: sum_pairs W dz_k^2 per input dimension, operands again loaded once per dimension
-    for (int k = 0; k < d; k++) {
-      double xr[4], xc[4];
+  // row sums: over the 4 lanes of a row (tq); column sums: over the 8 lanes of a column (g) - fixed order
 #pragma unroll
-      for (int a = 0; a < 4; a++) xr[a] = xi[(tr + 16 * a) * ldx + k];
+  for (int i = 0; i < 4; i++) {
+    double v = rsum[i];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (tq == 0) rowp[wn * GRAD_T + wm * 32 + i * 8 + g] = v;
+  }
 #pragma unroll
-      for (int q = 0; q < 4; q++) xc[q] = xj[(tc + 16 * q) * ldx + k];
-      double v = 0.0;
+  for (int j = 0; j < 2; j++)
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+    for (int e = 0; e < 2; e++) {
+      double v = csum[j][e];
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const double dz = xr[a] - xc[q]; v = fma(Wv[a][q] * dz, dz, v); }
+      for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (g == 0) colp[wm * GRAD_T + wn * 16 + j * 8 + tq * 2 + e] = v;
+    }
+  __syncthreads();
+  // ---- P = W Zj: warp owns rows warp * 8 .. + 8; per 8-dimension fragment one 64-deep DMMA chain ----
+  // contribution of element (row, k): zi[row][k] (R_row zi[row][k] - 2 P[row][k]) + C_row zj[row][k]^2
+  if (d > 0) {
+    const int row = warp * 8 + g;
+    const double Rr = (rowp[row] + rowp[GRAD_T + row]) + (rowp[2 * GRAD_T + row] + rowp[3 * GRAD_T + row]);
+    const double Cr = colp[row] + colp[GRAD_T + row];
+    for (int nf = 0; nf < nz; nf++) {
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll 4
+      for (int kk = 0; kk < GRAD_T; kk += 4)
+        dmma884(p0, p1, Wsm[row * GRAD_LDW + kk + tq], zj[(kk + tq) * ldz + nf * 8 + g]);
+      const int k0 = nf * 8 + tq * 2;
+      const double2 zi2 = *reinterpret_cast<const double2*>(zi + row * ldz + k0);
+      const double2 zj2 = *reinterpret_cast<const double2*>(zj + row * ldz + k0);
+      double v0 = fma(zi2.x, fma(Rr, zi2.x, -2.0 * p0), Cr * zj2.x * zj2.x);
+      double v1 = fma(zi2.y, fma(Rr, zi2.y, -2.0 * p1), Cr * zj2.y * zj2.y);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[warp * (GRAD_DMAX + 1) + k] = v;
+      for (int o = 4; o < 32; o <<= 1) {             // sum over the 8 rows of the fragment (lanes with equal tq)
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      }
+      if (g == 0) {
+        if (k0 < d) red[warp * (GRAD_DMAX + 1) + k0] = v0 * amp;
+        if (k0 + 1 < d) red[warp * (GRAD_DMAX + 1) + k0 + 1] = v1 * amp;
+      }
     }
   }
   {
@@ -754,10 +842,11 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
     if (lane == 0) red[warp * (GRAD_DMAX + 1) + GRAD_DMAX] = v;
   }
   __syncthreads();
-  for (int k = tid; k <= d; k += 256) {
-    const int kk = (k == d) ? GRAD_DMAX : k;
+  double* part = p.partial + ((long long)b * p.npart + t) * (p.d + 1);
+  for (int k = tid; k <= p.d; k += 256) {
+    const int kk = (k == p.d) ? GRAD_DMAX : k;
     double s = 0.0;
-    if (k == d || p.have_k)
+    if (k == p.d || p.have_k)
       for (int wv = 0; wv < 8; wv++) s += red[wv * (GRAD_DMAX + 1) + kk];
     part[k] = s;
   }

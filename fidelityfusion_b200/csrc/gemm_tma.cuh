@@ -35,7 +35,8 @@ constexpr int TG_THREADS = (TG_CONSUMER_WARPS + 4) * 32;             // 2 consum
 constexpr int TG_REGS_PRODUCER = 40, TG_REGS_CONSUMER = 232;
 constexpr int TG_PANEL_BYTES = TG_BM * TG_BK * 8;                       // 16 KB per operand per stage
 constexpr int TG_STAGE_BYTES = 2 * TG_PANEL_BYTES;
-constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+constexpr int TG_TILE_RING = 8;                                         // > TG_STAGES: the producer is at most TG_STAGES tiles ahead
+constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/ + 4 * TG_TILE_RING;
 
 struct TmaGemmParams {
   double* C;
@@ -44,6 +45,9 @@ struct TmaGemmParams {
   int M, N, K, inner;
   double alpha, beta;
   int lower_only, kmode, heavy_first;
+  int tiles, total;          // tiles per problem, work items of the launch (tiles x problems); grid.x <= total
+  unsigned int* sched;       // NULL: one work item per CTA (grid.x == total).  Else {next, done} counters, both zero at
+                             // launch and reset by the last CTA: CTAs fetch further work items as they finish
 };
 
 __device__ __forceinline__ uint32_t tg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -93,6 +97,36 @@ struct TgLive {
   }
 };
 
+// Work item w of a launch -> problem (zo, zi), tile (ti, tj) and the K range of that tile (same ordering rules as
+// gemm_dmma_kernel).  Items are numbered tile-fastest, so the tiles of one problem are in flight together and share
+// their operand panels through L2.
+struct TgTile { int ti, tj, k_lo, k_hi, zo, zi; };
+__device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int w) {
+  TgTile r;
+  const int z = w / p.tiles;
+  int t = w - z * p.tiles;
+  const int tiles_m = p.M / TG_BM, tiles_n = p.N / TG_BN;
+  if (p.lower_only) {
+    if (p.heavy_first && p.kmode != K_GE_ROW) t = p.tiles - 1 - t;
+    r.ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (r.ti * (r.ti + 1) / 2 > t) --r.ti;
+    while ((r.ti + 1) * (r.ti + 2) / 2 <= t) ++r.ti;
+    r.tj = t - r.ti * (r.ti + 1) / 2;
+  } else {
+    if (p.heavy_first && (p.kmode == K_LE_ROW || p.kmode == K_LE_COL)) t = p.tiles - 1 - t;
+    if (p.kmode == K_LE_COL || p.kmode == K_GE_COL) { r.tj = t / tiles_m; r.ti = t - r.tj * tiles_m; }
+    else { r.ti = t / tiles_n; r.tj = t - r.ti * tiles_n; }
+  }
+  const int i0 = r.ti * TG_BM, j0 = r.tj * TG_BN;
+  r.k_lo = 0; r.k_hi = p.K;
+  if (p.kmode == K_LE_ROW) r.k_hi = min(p.K, i0 + TG_BM);
+  else if (p.kmode == K_LE_COL) r.k_hi = min(p.K, j0 + TG_BN);
+  else if (p.kmode == K_GE_COL) r.k_lo = j0;
+  else if (p.kmode == K_GE_ROW) r.k_lo = i0;
+  r.zo = z / p.inner; r.zi = z - r.zo * p.inner;
+  return r;
+}
+
 // A_KMAJ: A(i,p) = A[i*lda + p]  else  A(i,p) = A[p*lda + i];   B_KMAJ: B(p,j) = B[j*ldb + p]  else  B[p*ldb + j]
 template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(TG_THREADS, 1)
@@ -101,31 +135,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t smem_base = (tg_smem_u32(tg_smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B panels need 1024-B alignment
   const uint32_t bar_base = smem_base + TG_STAGES * TG_STAGE_BYTES;           // full[s] at +8s, empty[s] at +64+8s
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  // ---- tile coordinates (same ordering rules as gemm_dmma_kernel) ------------------------------
-  const int tiles_m = p.M / TG_BM, tiles_n = p.N / TG_BN;
-  int t = blockIdx.x, ti, tj;
-  if (p.lower_only) {
-    const int total = tiles_m * (tiles_m + 1) / 2;
-    if (p.heavy_first && p.kmode != K_GE_ROW) t = total - 1 - t;
-    ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while (ti * (ti + 1) / 2 > t) --ti;
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    tj = t - ti * (ti + 1) / 2;
-  } else {
-    const int total = tiles_m * tiles_n;
-    if (p.heavy_first && (p.kmode == K_LE_ROW || p.kmode == K_LE_COL)) t = total - 1 - t;
-    if (p.kmode == K_LE_COL || p.kmode == K_GE_COL) { tj = t / tiles_m; ti = t - tj * tiles_m; }
-    else { ti = t / tiles_n; tj = t - ti * tiles_n; }
-  }
-  const int i0 = ti * TG_BM, j0 = tj * TG_BN;
-  int k_lo = 0, k_hi = p.K;
-  if (p.kmode == K_LE_ROW) k_hi = min(p.K, i0 + TG_BM);
-  else if (p.kmode == K_LE_COL) k_hi = min(p.K, j0 + TG_BN);
-  else if (p.kmode == K_GE_COL) k_lo = j0;
-  else if (p.kmode == K_GE_ROW) k_lo = i0;
-  const int KT = (k_hi - k_lo) / TG_BK;
-  const int zo = blockIdx.z / p.inner, zi = blockIdx.z - zo * p.inner;
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(tg_smem_raw + (smem_base - tg_smem_u32(tg_smem_raw)) +
+                                                            TG_STAGES * TG_STAGE_BYTES + 128);
 
   if (tid == 0) {
     for (int s = 0; s < TG_STAGES; s++) {
@@ -142,17 +153,44 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == TG_CONSUMER_WARPS && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-      for (int kt = 0; kt < KT; kt++) {
-        const int s = kt % TG_STAGES;
-        const uint32_t full = bar_base + 8 * s, empty = bar_base + 64 + 8 * s;
-        if (kt >= TG_STAGES) tg_mbar_wait(empty, ((kt / TG_STAGES) - 1) & 1);
-        tg_mbar_expect_tx(full, TG_STAGE_BYTES);
-        const uint32_t dstA = smem_base + s * TG_STAGE_BYTES, dstB = dstA + TG_PANEL_BYTES;
-        const int k0 = k_lo + kt * TG_BK;
-        if (A_KMAJ) tg_tma_4d(dstA, &mapA, full, k0, i0, zi, zo);
-        else tg_tma_5d(dstA, &mapA, full, 0, k0, i0 >> 3, zi, zo);
-        if (B_KMAJ) tg_tma_4d(dstB, &mapB, full, k0, j0, zi, zo);
-        else tg_tma_5d(dstB, &mapB, full, 0, k0, j0 >> 3, zi, zo);
+      // Work items: the CTA's own (blockIdx.x), then - persistent grid - whatever the launch-wide counter hands out
+      // next, so SMs take tiles as they free up exactly like the hardware CTA scheduler would, minus the per-CTA launch,
+      // barrier-init and first-load latency.  The id of every further tile is published to the MMA warps through
+      // tile_ring (written before the expect_tx arrive of the tile's first stage, read after the wait on it); -1 ends.
+      int it = 0;                                   // k-steps issued so far: the stage ring runs on across tiles
+      int w = blockIdx.x;
+      for (int n = 0;; n++) {
+        unsigned int fetched = 0;
+        if (p.sched) fetched = atomicAdd(p.sched, 1u);      // next item, requested before this one's loads are issued
+        const TgTile tl = tg_decode(p, w);
+        const int i0 = tl.ti * TG_BM, j0 = tl.tj * TG_BN;
+        const int KT = (tl.k_hi - tl.k_lo) / TG_BK;
+        for (int kt = 0; kt < KT; kt++, it++) {
+          const int s = it % TG_STAGES;
+          const uint32_t full = bar_base + 8 * s, empty = bar_base + 64 + 8 * s;
+          if (it >= TG_STAGES) tg_mbar_wait(empty, ((it / TG_STAGES) - 1) & 1);
+          if (kt == 0 && n > 0) tile_ring[n % TG_TILE_RING] = w;
+          tg_mbar_expect_tx(full, TG_STAGE_BYTES);
+          const uint32_t dstA = smem_base + s * TG_STAGE_BYTES, dstB = dstA + TG_PANEL_BYTES;
+          const int k0 = tl.k_lo + kt * TG_BK;
+          if (A_KMAJ) tg_tma_4d(dstA, &mapA, full, k0, i0, tl.zi, tl.zo);
+          else tg_tma_5d(dstA, &mapA, full, 0, k0, i0 >> 3, tl.zi, tl.zo);
+          if (B_KMAJ) tg_tma_4d(dstB, &mapB, full, k0, j0, tl.zi, tl.zo);
+          else tg_tma_5d(dstB, &mapB, full, 0, k0, j0 >> 3, tl.zi, tl.zo);
+        }
+        if (!p.sched) break;
+        const long long wn = (long long)gridDim.x + fetched;
+        if (wn >= p.total) {
+          // end marker: takes one stage slot (no data), the MMA warps leave without releasing it
+          const int s = it % TG_STAGES;
+          if (it >= TG_STAGES) tg_mbar_wait(bar_base + 64 + 8 * s, ((it / TG_STAGES) - 1) & 1);
+          tile_ring[(n + 1) % TG_TILE_RING] = -1;
+          tg_mbar_arrive(bar_base + 8 * s);
+          // every CTA fetches exactly one item past the end: the last one to get there rearms the counters
+          if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) { p.sched[0] = 0u; p.sched[1] = 0u; __threadfence(); }
+          break;
+        }
+        w = (int)wn;
       }
     }
     return;
@@ -168,6 +206,35 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int wm = warp >> 2, wn = (warp & 3) ^ (wm ? 3 : 0);
   const int g = lane >> 2, tq = lane & 3;
   constexpr int MT = 8, NT = 4;
+  // per-thread fragment offsets inside a stage (bytes)
+  const uint32_t swz_h = (uint32_t)((tq >> 1) ^ g);        // k-major: 16-B chunk index = (2 kk + (tq>>1)) ^ (row & 7)
+  const uint32_t a_off = A_KMAJ ? (uint32_t)((wm * 8 + g) * 128 + ((tq & 1) << 3))
+                                : (uint32_t)(wm * 1024 + tq * 64 + g * 8);
+  const uint32_t b_off = TG_PANEL_BYTES + (B_KMAJ ? (uint32_t)((wn * 8 + g) * 128 + ((tq & 1) << 3))
+                                                  : (uint32_t)(wn * 1024 + tq * 64 + g * 8));
+  double af[2][MT], bf[2][NT];
+  auto load_frags = [&](int buf, uint32_t stage_base, int kk) {
+    const uint32_t kx = A_KMAJ || B_KMAJ ? (((uint32_t)(2 * kk) ^ swz_h) << 4) : 0u;
+    const uint32_t pa = stage_base + a_off + (A_KMAJ ? kx : (uint32_t)(kk * 256));
+    const uint32_t pb = stage_base + b_off + (B_KMAJ ? kx : (uint32_t)(kk * 256));
+#pragma unroll
+    for (int i = 0; i < MT; i++) af[buf][i] = tg_lds(pa + i * 2048);
+#pragma unroll
+    for (int j = 0; j < NT; j++) bf[buf][j] = tg_lds(pb + j * 4096);
+  };
+
+  const double alpha = p.alpha, beta = p.beta;
+  // one tile per CTA: beta C enters through the accumulators (read overlapped with the first panel loads); persistent
+  // grid: through the epilogue
+  const bool init_from_c = (beta != 0.0) && (alpha != 0.0) && !p.sched;
+  const int role = wm * 4 + wn;
+  double acc[MT][NT][2];
+  int it0 = 0;                                     // k-steps consumed before this tile (the stage ring runs on across tiles)
+  int w = blockIdx.x;
+  for (int n = 0;; n++) {
+  const TgTile tl = tg_decode(p, w);
+  const int ti = tl.ti, tj = tl.tj, i0 = ti * TG_BM, j0 = tj * TG_BN, k_hi = tl.k_hi;
+  const int KT = (tl.k_hi - tl.k_lo) / TG_BK;
   // ---- structural zeros.  A kmode says an operand is TRIANGULAR (ffgp.h): besides shortening the K range of the tile,
   // inside the one 128-deep K block that straddles the diagonal a k4 step only touches fragments whose rows (columns)
   // reach it; and a lower_only diagonal tile is symmetric, only fragments on/below its diagonal are produced (the rest
@@ -180,11 +247,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   else if (p.kmode == K_GE_COL) { tri_mode = 3; tri_kt0 = 0; }
   else if (p.kmode == K_GE_ROW) { tri_mode = 4; tri_kt0 = 0; }
   const int sym_thr = sym_diag ? 0 : -64;                 // fragment (i, j) is produced iff 2 i + wm - 4 j - wn >= sym_thr
-  double* __restrict__ Cg = p.C + (long long)zo * p.sC + (long long)zi * p.iC;
-  const double alpha = p.alpha, beta = p.beta;
+  double* __restrict__ Cg = p.C + (long long)tl.zo * p.sC + (long long)tl.zi * p.iC;
 
-  double acc[MT][NT][2];
-  const bool init_from_c = (beta != 0.0) && (alpha != 0.0);
   if (init_from_c) {
     // C is read while the first panels are in flight: acc starts at (beta/alpha) C, the epilogue multiplies by alpha
     const double r = beta / alpha;
@@ -207,33 +271,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       for (int j = 0; j < NT; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   }
 
-  // per-thread fragment offsets inside a stage (bytes)
-  const uint32_t swz_h = (uint32_t)((tq >> 1) ^ g);        // k-major: 16-B chunk index = (2 kk + (tq>>1)) ^ (row & 7)
-  const uint32_t a_off = A_KMAJ ? (uint32_t)((wm * 8 + g) * 128 + ((tq & 1) << 3))
-                                : (uint32_t)(wm * 1024 + tq * 64 + g * 8);
-  const uint32_t b_off = TG_PANEL_BYTES + (B_KMAJ ? (uint32_t)((wn * 8 + g) * 128 + ((tq & 1) << 3))
-                                                  : (uint32_t)(wn * 1024 + tq * 64 + g * 8));
-  double af[2][MT], bf[2][NT];
-  auto load_frags = [&](int buf, uint32_t stage_base, int kk) {
-    const uint32_t kx = A_KMAJ || B_KMAJ ? (((uint32_t)(2 * kk) ^ swz_h) << 4) : 0u;
-    const uint32_t pa = stage_base + a_off + (A_KMAJ ? kx : (uint32_t)(kk * 256));
-    const uint32_t pb = stage_base + b_off + (B_KMAJ ? kx : (uint32_t)(kk * 256));
-#pragma unroll
-    for (int i = 0; i < MT; i++) af[buf][i] = tg_lds(pa + i * 2048);
-#pragma unroll
-    for (int j = 0; j < NT; j++) bf[buf][j] = tg_lds(pb + j * 4096);
-  };
-
   if (KT > 0) {
-    tg_mbar_wait(bar_base, 0);
-    load_frags(0, smem_base, 0);
+    tg_mbar_wait(bar_base + 8 * (it0 % TG_STAGES), (it0 / TG_STAGES) & 1);
+    load_frags(0, smem_base + (it0 % TG_STAGES) * TG_STAGE_BYTES, 0);
   }
   // One k-step (16 deep = 4 k4 steps) with the compile-time set of live fragments `Lv`: straight-line DMMAs, no
   // per-instruction predicates (a first version predicated every DMMA: the compiler guards each with WARPSYNC + a
   // chain of ISETPs and the "skipped" work cost more than doing it, profiles/r01_c5_trisk_v1.txt).
   auto kt_body = [&](auto lv, int kt) {
     using Lv = decltype(lv);
-    const int s = kt % TG_STAGES;
+    const int s = (it0 + kt) % TG_STAGES;
     const uint32_t stage_base = smem_base + s * TG_STAGE_BYTES;
 #pragma unroll
     for (int kk = 0; kk < TG_BK / 4; kk++) {
@@ -241,8 +288,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (kk < TG_BK / 4 - 1) {
         load_frags(nxt, stage_base, kk + 1);
       } else if (kt + 1 < KT) {
-        const int s2 = (kt + 1) % TG_STAGES;
-        tg_mbar_wait(bar_base + 8 * s2, ((kt + 1) / TG_STAGES) & 1);
+        const int s2 = (it0 + kt + 1) % TG_STAGES;
+        tg_mbar_wait(bar_base + 8 * s2, ((it0 + kt + 1) / TG_STAGES) & 1);
         load_frags(nxt, smem_base + s2 * TG_STAGE_BYTES, 0);
       }
 #pragma unroll
@@ -257,7 +304,6 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   };
-  const int role = wm * 4 + wn;
   for (int kt = 0; kt < KT; kt++) {
     // variant of this k-step (warp-uniform): 0 dense | 1..7 i >= v | 8..14 i < v-7 | 15..17 j >= v-14 | 18..20 j < v-17 |
     // 21..28 symmetric diagonal tile, by warp role.  Ranges are the union over the four k4 steps of the k-step.
@@ -322,18 +368,22 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (2 * i + wm - 4 * j - wn < sym_thr) continue;      // above the diagonal of a symmetric tile: not produced
       const int col = j0 + (4 * j + wn) * 8 + tq * 2;
       double2* dst = reinterpret_cast<double2*>(Cg + (long long)row * p.ldc + col);
-      double2 v;
-      if (init_from_c || beta == 0.0) {
-        v.x = alpha * acc[i][j][0];
-        v.y = alpha * acc[i][j][1];
-      } else {                                  // alpha == 0, beta != 0
+      double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+      if (beta != 0.0 && !init_from_c) {        // the 64 loads of a thread are independent: one memory latency per tile
         const double2 o = *dst;
-        v.x = beta * o.x;
-        v.y = beta * o.y;
+        v.x = fma(beta, o.x, v.x);
+        v.y = fma(beta, o.y, v.y);
       }
       *dst = v;
     }
   }
+  it0 += KT;
+  if (!p.sched) break;
+  // next work item of this CTA: its id is valid once the first stage of the tile (or the end marker) has been posted
+  tg_mbar_wait(bar_base + 8 * (it0 % TG_STAGES), (it0 / TG_STAGES) & 1);
+  w = tile_ring[(n + 1) % TG_TILE_RING];
+  if (w < 0) break;
+  }   // tile loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,7 +434,7 @@ inline bool tg_make_map(CUtensorMap* map, const double* base, bool kmaj, int row
 }
 
 template <bool A_KMAJ, bool B_KMAJ>
-cudaError_t launch_gemm_tma_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TmaGemmParams& tp, int tiles, int batch,
+cudaError_t launch_gemm_tma_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TmaGemmParams& tp, int grid,
                                 cudaStream_t st) {
   auto kern = gemm_tma_kernel<A_KMAJ, B_KMAJ>;
   static bool attr_set = false;
@@ -393,12 +443,29 @@ cudaError_t launch_gemm_tma_cfg(const CUtensorMap& mA, const CUtensorMap& mB, co
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<dim3(tiles, 1, batch), TG_THREADS, TG_SMEM_BYTES, st>>>(mA, mB, tp);
+  kern<<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(mA, mB, tp);
   return cudaGetLastError();
 }
 
 // Returns cudaErrorNotSupported when the problem cannot go through the TMA kernel (caller uses gemm_dmma_kernel).
-inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p, int batch_outer, cudaStream_t st) {
+// Work-item counters of the persistent grids ({next, done} per slot), zero at load and rearmed by each launch itself.
+constexpr int TG_SCHED_SLOTS = 64;
+__device__ unsigned int g_tg_sched[2 * TG_SCHED_SLOTS];
+inline unsigned int* tg_sched_base() {
+  static unsigned int* base[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  unsigned int*& b = base[dev & 63];
+  if (!b && cudaGetSymbolAddress((void**)&b, g_tg_sched) != cudaSuccess) b = nullptr;
+  return b;
+}
+
+// `persistent_ctas` > 0: that many CTAs pull work items from a launch-wide counter, so the TMA producer streams the next
+// tile's panels while the MMA warps finish and store the current one (no per-tile launch / barrier-init / first-load
+// latency; batched small problems, where a tile is only 64-256 deep).  0: one CTA per work item, heavy tiles first -
+// the hardware scheduler balances and SMs free up for a high-priority panel chain as tiles retire.
+inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p, int batch_outer, cudaStream_t st,
+                                   int persistent_ctas = 0) {
   if (p.M % TG_BM || p.N % TG_BN || p.K % TG_BK || p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorNotSupported;
   if (((uintptr_t)p.C & 15) || (p.ldc & 1)) return cudaErrorNotSupported;
   CUtensorMap mA, mB;
@@ -409,11 +476,23 @@ inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p
   tp.alpha = p.alpha; tp.beta = p.beta; tp.lower_only = p.lower_only; tp.kmode = p.kmode; tp.heavy_first = p.heavy_first;
   const int tm = p.M / TG_BM, tn = p.N / TG_BN;
   const int tiles = p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
-  const int batch = batch_outer * p.inner;
-  if (a_kmaj && b_kmaj) return launch_gemm_tma_cfg<true, true>(mA, mB, tp, tiles, batch, st);
-  if (a_kmaj && !b_kmaj) return launch_gemm_tma_cfg<true, false>(mA, mB, tp, tiles, batch, st);
-  if (!a_kmaj && b_kmaj) return launch_gemm_tma_cfg<false, true>(mA, mB, tp, tiles, batch, st);
-  return launch_gemm_tma_cfg<false, false>(mA, mB, tp, tiles, batch, st);
+  const long long total = (long long)tiles * batch_outer * p.inner;
+  if (total > 0x7fffffffLL) return cudaErrorNotSupported;
+  tp.tiles = tiles; tp.total = (int)total;
+  int grid = (int)total;
+  tp.sched = nullptr;
+  if (persistent_ctas > 0 && total > persistent_ctas) {
+    unsigned int* base = tg_sched_base();
+    if (base) {
+      static unsigned int seq = 0;                       // a slot is reused 64 launches later: long after its kernel ended
+      tp.sched = base + 2 * (seq++ % TG_SCHED_SLOTS);
+      grid = persistent_ctas;
+    }
+  }
+  if (a_kmaj && b_kmaj) return launch_gemm_tma_cfg<true, true>(mA, mB, tp, grid, st);
+  if (a_kmaj && !b_kmaj) return launch_gemm_tma_cfg<true, false>(mA, mB, tp, grid, st);
+  if (!a_kmaj && b_kmaj) return launch_gemm_tma_cfg<false, true>(mA, mB, tp, grid, st);
+  return launch_gemm_tma_cfg<false, false>(mA, mB, tp, grid, st);
 }
 
 }  // namespace ffgp

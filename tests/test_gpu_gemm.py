@@ -1,0 +1,18 @@
+"""ffgp_gemm_f64 (include/ffgp.h) against torch.matmul: every operand layout, K-range mode, lower_only and batch level,
+once with one CTA per tile and once with the persistent grid the batched path uses (tools/check_gemm.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('persist', ['0', '2'])
+def test_gemm_all_modes(persist):
+    env = dict(os.environ, FFGP_PERSIST=persist)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'check_gemm.py')], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]

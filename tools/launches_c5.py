@@ -34,4 +34,4 @@ for _ in range(a.evals):
     r = batched_cigp_eval(x, y, ls, sv, lb, xs)
 e1.record()
 torch.cuda.synchronize()
-print('ms per eval', e0.elapsed_time(e1) / a.evals, 'nll checksum', float(r['nll'].sum()))
+print('ms per eval', e0.elapsed_time(e1) / a.evals, 'nll checksum', float(r['nll'].sum()), 'input checksum', float(x.sum() + y.sum() + xs.sum()))
