@@ -525,10 +525,12 @@ static cudaError_t ensure_attrs() {
   if (g_attr_done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(potrf_trtri_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem_doubles(GRAD_DMAX) * 8);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
+  for (auto kern : {grad_contract_kernel<false>, grad_contract_kernel<true>}) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem_doubles(GRAD_DMAX) * 8);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
   g_attr_done = true;
   return cudaSuccess;
 }
@@ -741,7 +743,8 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
       gp.g_diag = g_diag ? g_diag + (long long)b0 * n : nullptr; gp.sgd = n;
       gp.G_out = g_sigma ? g_sigma + (long long)b0 * n * n : nullptr; gp.sGo = (long long)n * n;
       gp.have_k = amp ? 1 : 0;
-      grad_contract_kernel<<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
+      if (gp.G_out) grad_contract_kernel<true><<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
+      else grad_contract_kernel<false><<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
       FFGP_LAUNCHED();
       if (amp) {
         grad_finish_kernel<<<dim3(d + 1, nb), 256, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,

@@ -654,6 +654,38 @@ __host__ __device__ inline size_t grad_smem_doubles(int d) {
 // with R / C the row / column sums of the tile's W.  The previous version evaluated (z_ik - z_jk)^2 pair by pair and
 // dimension by dimension twice (5 d + 45 FP64 instructions per pair, FP64-FMA bound: 0.88 ms per 512 problems of
 // N = 512, d = 8, profiles/r01_launches_c5_v6.csv); this one needs about 35 per pair independent of d.
+// exp(x) for x <= 0, branch-free: n = rint(x log2 e) by the 1.5 * 2^52 trick, r = x - n ln 2 in two pieces (|r| <= 0.347),
+// degree-13 Taylor polynomial (truncation (ln 2 / 2)^14 / 14! = 4e-18), scaling through the exponent field; results
+// below 2^-1020 are flushed to zero.  Error <= 1 ulp of the result like exp(), without its special-case paths, so the
+// 16 evaluations of a thread stay straight-line code.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double MAGIC = 6755399441055744.0;
+  x = fmax(x, -800.0);                               // exp(-800) is flushed to zero below; keeps n in int range
+  const double t = fma(x, 1.4426950408889634074, MAGIC);
+  const int n = __double2loint(t);
+  const double nf = t - MAGIC;
+  double r = fma(nf, -6.93147180369123816490e-01, x);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821614599e-10;              // 1/13!
+  q = fma(q, r, 2.0876756987868098979e-09);          // 1/12!
+  q = fma(q, r, 2.5052108385441718775e-08);          // 1/11!
+  q = fma(q, r, 2.7557319223985890653e-07);          // 1/10!
+  q = fma(q, r, 2.7557319223985892511e-06);          // 1/9!
+  q = fma(q, r, 2.4801587301587301566e-05);          // 1/8!
+  q = fma(q, r, 1.9841269841269841253e-04);          // 1/7!
+  q = fma(q, r, 1.3888888888888889419e-03);          // 1/6!
+  q = fma(q, r, 8.3333333333333332177e-03);          // 1/5!
+  q = fma(q, r, 4.1666666666666664354e-02);          // 1/4!
+  q = fma(q, r, 1.6666666666666665741e-01);          // 1/3!
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const double scale = __hiloint2double((max(n, -1021) + 1023) << 20, 0);
+  return n < -1020 ? 0.0 : q * scale;
+}
+
+// GOUT: also write the full symmetric dNLL/dSigma (covariance-input mode); kept out of the common instantiation.
+template <bool GOUT>
 __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) {
   extern __shared__ __align__(16) double gsm[];
   const int b = blockIdx.y;
@@ -694,20 +726,21 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
       }
     }
   }
-  if (d > 0) {
-    for (int e = tid; e < 2 * GRAD_T * dz; e += 256) {
-      const int which = e / (GRAD_T * dz), r = (e / dz) % GRAD_T, k = e % dz;
-      const int gi = (which ? j0 : i0) + r;
-      const double v = (gi < p.n && k < d) ? (x[(long long)gi * d + k] - x[k]) * w[k] : 0.0;
-      (which ? zj : zi)[r * ldz + k] = v;
+  if (d > 0) {          // 4 threads per row, strided over the (padded) dimensions: no index divisions
+    const int r = tid >> 2, gi = i0 + r, gj = j0 + r;
+    for (int k = tid & 3; k < dz; k += 4) {
+      const bool kin = k < d;
+      const double x0 = kin ? x[k] : 0.0, wk = kin ? w[k] : 0.0;
+      zi[r * ldz + k] = (kin && gi < p.n) ? (x[(long long)gi * d + k] - x0) * wk : 0.0;
+      zj[r * ldz + k] = (kin && gj < p.n) ? (x[(long long)gj * d + k] - x0) * wk : 0.0;
     }
   }
   if (!p.src_is_G) {
     const double* al = p.alpha + b * p.salpha;
-    for (int e = tid; e < 2 * GRAD_T * 8; e += 256) {
-      const int which = e / (GRAD_T * 8), r = (e / 8) % GRAD_T, c = e % 8;
-      const int gi = (which ? j0 : i0) + r;
-      (which ? aj : ai)[r * 8 + c] = (gi < p.n && c < p.D) ? al[(long long)gi * p.D + c] : 0.0;
+    const int r = tid >> 2;
+    for (int c = tid & 3; c < 8; c += 4) {
+      ai[r * 8 + c] = (i0 + r < p.n && c < p.D) ? al[(long long)(i0 + r) * p.D + c] : 0.0;
+      aj[r * 8 + c] = (j0 + r < p.n && c < p.D) ? al[(long long)(j0 + r) * p.D + c] : 0.0;
     }
   }
   __syncthreads();
@@ -750,7 +783,7 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const double sq = fmax(nrm[r] + nrm[GRAD_T + c0 + e] - 2.0 * acc[i][j][e], 0.0);
-        wv[i][j][e] = exp(-0.5 * sq);
+        wv[i][j][e] = exp_nonpos(-0.5 * sq);
       }
     }
   }
@@ -769,11 +802,12 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) 
         const bool valid = gi < p.n && gj <= gi;
         double G = sv[e];
         if (!p.src_is_G) {
-          double aa = 0.0;
-          for (int cc = 0; cc < p.D; cc++) aa = fma(ai[r * 8 + cc], aj[c * 8 + cc], aa);
+          double aa = ai[r * 8] * aj[c * 8];
+          if (p.D > 1)
+            for (int cc = 1; cc < p.D; cc++) aa = fma(ai[r * 8 + cc], aj[c * 8 + cc], aa);
           G = 0.5 * ((double)p.D * G - aa);
         }
-        if (valid && p.G_out) {
+        if (GOUT && valid) {
           double* go = p.G_out + b * p.sGo;
           go[(long long)gi * p.n + gj] = G;
           go[(long long)gj * p.n + gi] = G;
