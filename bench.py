@@ -214,6 +214,36 @@ def kron_numbers(torch):
     return out
 
 
+def training_numbers(torch, iters=100):
+    """Device-side training loop at the reference's real size (N=300, d=2: FidelityFusion_Models/log/AR/
+    train.log, 11 ms/epoch on the reference's CPU): ms per epoch (zero_grad -> NLL -> backward -> Adam.step) of the
+    eager loop with torch.optim.Adam and of the CUDA-graph replay with the fused Adam kernel."""
+    from fidelityfusion_b200.GaussianProcess.cigp_v10 import cigp
+    from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
+    from fidelityfusion_b200.training import GraphedTrainer
+    g = torch.Generator().manual_seed(300)
+    x = torch.rand(300, 2, generator=g, dtype=torch.float64).cuda()
+    y = (torch.sin(3 * x.sum(1, keepdim=True)) + 0.1 * torch.randn(300, 1, generator=g, dtype=torch.float64).cuda())
+    m = cigp(ARDKernel(2), 1.0).double().cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=0.01)
+
+    def it():
+        opt.zero_grad(); loss = -m.negative_log_likelihood(x, y); loss.backward(); opt.step()
+    for _ in range(5):
+        it()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(iters):
+        it()
+    torch.cuda.synchronize(); eager = (time.perf_counter() - t0) / iters * 1e3
+    m2 = cigp(ARDKernel(2), 1.0).double().cuda()
+    tr = GraphedTrainer(lambda: -m2.negative_log_likelihood(x, y), m2.parameters(), lr=0.01, history=2 * iters + 8)
+    tr.run(5); torch.cuda.synchronize(); t0 = time.perf_counter()
+    tr.run(iters, check=False); torch.cuda.synchronize(); graphed = (time.perf_counter() - t0) / iters * 1e3
+    tr.check()
+    return {'config': 'cigp + ARDKernel, N=300, d=2, D=1, Adam', 'eager_torch_adam_ms_per_epoch': eager,
+            'graph_replay_fused_adam_ms_per_epoch': graphed, 'final_loss': float(tr.losses()[-1])}
+
+
 def measure_dgemm_peak(torch):
     """FP64 roofline denominator: cuBLAS DGEMM 8192^3 through torch.matmul, best of 10 (MEASURED_PEAKS.json
     has no fp64 entry)."""
@@ -424,6 +454,10 @@ def main():
             line['kron'] = kron_numbers(torch)
         except Exception as e:                          # secondary numbers must never cost the headline line
             line['kron'] = {'error': repr(e)[:300]}
+        try:
+            line['training'] = training_numbers(torch)
+        except Exception as e:
+            line['training'] = {'error': repr(e)[:300]}
     if batched is not None:
         batched['roofline_frac'] = batched['tflops_alg'] / world / peak_tflops if peak_tflops else None
         line['batched'] = batched

@@ -11,6 +11,7 @@
 #include "gemm_tma.cuh"
 #include "xgrad_kernels.cuh"
 #include "acq_kernels.cuh"
+#include "train_kernels.cuh"
 
 namespace ffgp {
 
@@ -990,6 +991,19 @@ int ffgp_acquisition_f64(const double* mean, const double* var, int m, int kind,
   p.std_min = 1e-9; p.two_pi = 2.0 * 3.1415926;          /* DMF_acq.py:7,98,121 */
   p.round_f32 = round_f32; p.score = score; p.d_mean = d_mean; p.d_var = d_var;
   acq_kernel<<<(m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  FFGP_LAUNCHED();
+  return 0;
+}
+
+
+int ffgp_adam_step_f64(void* const* table, const int* sizes, int ntensors, double lr, double beta1, double beta2,
+                       double eps, int maximize, const double* loss, double* loss_hist, int hist_cap, void* stream) {
+  if (!table || !sizes) return fail(-1, "ffgp_adam_step_f64: null pointer");
+  if (ntensors <= 0) return fail(-2, "ffgp_adam_step_f64: ntensors must be positive");
+  if (!(lr >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0))
+    return fail(-2, "ffgp_adam_step_f64: bad hyper-parameter");
+  adam_step_kernel<<<ntensors, 256, 0, (cudaStream_t)stream>>>(table, sizes, lr, beta1, beta2, eps, maximize, loss, loss_hist,
+                                                             loss_hist ? hist_cap : 0);
   FFGP_LAUNCHED();
   return 0;
 }

@@ -35,6 +35,36 @@ struct KernelMatrixParams {
   int bounded;                            // K is the caller's exact [n1][n2] array: predicated scalar stores
 };
 
+// exp(x) for x <= 0 (and small positive x), branch-free: n = rint(x log2 e) by the 1.5 * 2^52 trick, r = x - n ln 2 in two pieces (|r| <= 0.347),
+// degree-13 Taylor polynomial (truncation (ln 2 / 2)^14 / 14! = 4e-18), scaling through the exponent field; results
+// below 2^-1020 are flushed to zero.  Error <= 1 ulp of the result like exp(), without its special-case paths, so the
+// 16 evaluations of a thread stay straight-line code.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double MAGIC = 6755399441055744.0;
+  x = fmax(x, -800.0);                               // exp(-800) is flushed to zero below; keeps n in int range
+  const double t = fma(x, 1.4426950408889634074, MAGIC);
+  const int n = __double2loint(t);
+  const double nf = t - MAGIC;
+  double r = fma(nf, -6.93147180369123816490e-01, x);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821614599e-10;              // 1/13!
+  q = fma(q, r, 2.0876756987868098979e-09);          // 1/12!
+  q = fma(q, r, 2.5052108385441718775e-08);          // 1/11!
+  q = fma(q, r, 2.7557319223985890653e-07);          // 1/10!
+  q = fma(q, r, 2.7557319223985892511e-06);          // 1/9!
+  q = fma(q, r, 2.4801587301587301566e-05);          // 1/8!
+  q = fma(q, r, 1.9841269841269841253e-04);          // 1/7!
+  q = fma(q, r, 1.3888888888888889419e-03);          // 1/6!
+  q = fma(q, r, 8.3333333333333332177e-03);          // 1/5!
+  q = fma(q, r, 4.1666666666666664354e-02);          // 1/4!
+  q = fma(q, r, 1.6666666666666665741e-01);          // 1/3!
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const double scale = __hiloint2double((max(n, -1021) + 1023) << 20, 0);
+  return n < -1020 ? 0.0 : q * scale;
+}
+
 __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixParams p) {
   constexpr int T = 64, DC = 16, LD = DC + 4;
   const int ti = blockIdx.y, tj = blockIdx.x, b = blockIdx.z;
@@ -95,6 +125,18 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixPa
   const double* dg = p.diag_add ? p.diag_add + b * p.sdiag : nullptr;
   const double* sg = p.sigma_add ? p.sigma_add + b * p.ssig : nullptr;
   double* K = p.K + b * p.sK;
+  // all 16 kernel values of the thread first, straight-line (the exp chains interleave), then the optional terms
+  double kv[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        double sq = nrm[0][wm * 32 + i * 8 + g] + nrm[1][wn * 16 + j * 8 + tq * 2 + e] - 2.0 * acc[i][j][e];
+        if (p.clamp) sq = fmax(sq, 0.0);
+        kv[i][j][e] = have_k ? fma(amp, exp_nonpos(-0.5 * sq), off) : off;
+      }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int r = wm * 32 + i * 8 + g, gi = i0 + r;
@@ -105,14 +147,8 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixPa
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int gj = j0 + c + e;
-        double v;
+        double v = kv[i][j][e];
         if (gi < p.n1 && gj < p.n2) {
-          v = off;
-          if (have_k) {
-            double sq = nrm[0][r] + nrm[1][c + e] - 2.0 * acc[i][j][e];
-            if (p.clamp) sq = fmax(sq, 0.0);
-            v += amp * exp(-0.5 * sq);
-          }
           if (sg) v += sg[(long long)gi * p.n2 + gj];
           if (dg && gi == gj) v += dg[gi];
         } else {
@@ -654,36 +690,6 @@ __host__ __device__ inline size_t grad_smem_doubles(int d) {
 // with R / C the row / column sums of the tile's W.  The previous version evaluated (z_ik - z_jk)^2 pair by pair and
 // dimension by dimension twice (5 d + 45 FP64 instructions per pair, FP64-FMA bound: 0.88 ms per 512 problems of
 // N = 512, d = 8, profiles/r01_launches_c5_v6.csv); this one needs about 35 per pair independent of d.
-// exp(x) for x <= 0, branch-free: n = rint(x log2 e) by the 1.5 * 2^52 trick, r = x - n ln 2 in two pieces (|r| <= 0.347),
-// degree-13 Taylor polynomial (truncation (ln 2 / 2)^14 / 14! = 4e-18), scaling through the exponent field; results
-// below 2^-1020 are flushed to zero.  Error <= 1 ulp of the result like exp(), without its special-case paths, so the
-// 16 evaluations of a thread stay straight-line code.
-__device__ __forceinline__ double exp_nonpos(double x) {
-  const double MAGIC = 6755399441055744.0;
-  x = fmax(x, -800.0);                               // exp(-800) is flushed to zero below; keeps n in int range
-  const double t = fma(x, 1.4426950408889634074, MAGIC);
-  const int n = __double2loint(t);
-  const double nf = t - MAGIC;
-  double r = fma(nf, -6.93147180369123816490e-01, x);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double q = 1.6059043836821614599e-10;              // 1/13!
-  q = fma(q, r, 2.0876756987868098979e-09);          // 1/12!
-  q = fma(q, r, 2.5052108385441718775e-08);          // 1/11!
-  q = fma(q, r, 2.7557319223985890653e-07);          // 1/10!
-  q = fma(q, r, 2.7557319223985892511e-06);          // 1/9!
-  q = fma(q, r, 2.4801587301587301566e-05);          // 1/8!
-  q = fma(q, r, 1.9841269841269841253e-04);          // 1/7!
-  q = fma(q, r, 1.3888888888888889419e-03);          // 1/6!
-  q = fma(q, r, 8.3333333333333332177e-03);          // 1/5!
-  q = fma(q, r, 4.1666666666666664354e-02);          // 1/4!
-  q = fma(q, r, 1.6666666666666665741e-01);          // 1/3!
-  q = fma(q, r, 0.5);
-  q = fma(q, r, 1.0);
-  q = fma(q, r, 1.0);
-  const double scale = __hiloint2double((max(n, -1021) + 1023) << 20, 0);
-  return n < -1020 ? 0.0 : q * scale;
-}
-
 // GOUT: also write the full symmetric dNLL/dSigma (covariance-input mode); kept out of the common instantiation.
 template <bool GOUT>
 __global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) {

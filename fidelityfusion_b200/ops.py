@@ -17,8 +17,28 @@ def _f64c(t):
     return t.detach().to(torch.float64).contiguous()
 
 
+_deferred_info = []      # (info tensor, what) recorded while a CUDA graph was being captured
+
+
+def flush_deferred_checks():
+    """Check (host sync) every factorisation status recorded under CUDA-graph capture since the last flush.  The info
+    buffers live in the graph's memory pool, so after any number of replays they hold the status of the LAST replay."""
+    pending, _deferred_info[:] = list(_deferred_info), []
+    for info, what in pending:
+        check_info(info, what)
+
+
 def check_info(info, what='cholesky'):
-    """Raise what torch.linalg.cholesky raises in the reference when Sigma is not PD."""
+    """Raise what torch.linalg.cholesky raises in the reference when Sigma is not PD.  Reading the status is a host
+    synchronisation, which is illegal while the stream is being captured into a CUDA graph (training.GraphedTrainer):
+    there the check is deferred to flush_deferred_checks()."""
+    if info.is_cuda and torch.cuda.is_current_stream_capturing():
+        _deferred_info.append((info, what))
+        return
+    if what == 'eigh':
+        if int(info.abs().sum()) != 0:
+            raise torch.linalg.LinAlgError('ffgp.eigh: Jacobi sweeps did not converge')
+        return
     bad = info.nonzero()
     if bad.numel():
         b = int(bad[0, 0])

@@ -125,8 +125,7 @@ def _eigh_launch(K):
 
 def _eigh_check(infos):
     """One device->host read for all the eigensolves of a call (torch.linalg.eigh raises on failure; so do we)."""
-    if int(torch.cat(infos).abs().sum()) != 0:
-        raise torch.linalg.LinAlgError('ffgp.eigh: Jacobi sweeps did not converge')
+    ops.check_info(torch.cat(infos), 'eigh')
 
 
 def eigh(K):

@@ -171,6 +171,21 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
                        double* out_mean, double* out_cov, int* info, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Device-side optimiser step.  torch.optim.Adam semantics (no weight decay, no amsgrad; operation
+ * order of torch/optim/adam.py::_single_tensor_adam) for `ntensors` parameter tensors in ONE launch; replaces the
+ * optimizer.step() of the reference's training loops (FidelityFusion_Models/CIGAR.py:96-106, AR_autoRegression.py:
+ * 120-140, GaussianProcess/cigp_v10.py:160-175, MFGP_ver2023May/mfgp_demo.py:40-48).
+ *   table  device array of 5*ntensors pointers: {param, grad, exp_avg, exp_avg_sq, step} per tensor (fp64, contiguous;
+ *          step is a device double[1] per tensor, zero before the first update and advanced by the kernel, so a
+ *          captured CUDA graph of one epoch replays with no host value changing between iterations)
+ *   sizes  device int[ntensors] element counts
+ *   loss / loss_hist (optional): loss_hist[step-1] = loss[0] for the first hist_cap steps (training curve without a
+ *          device-to-host read per iteration)
+ * --------------------------------------------------------------------------------------- */
+int ffgp_adam_step_f64(void* const* table, const int* sizes, int ntensors, double lr, double beta1, double beta2,
+                       double eps, int maximize, const double* loss, double* loss_hist, int hist_cap, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Cholesky factor and triangular inverse of `batch` SPD matrices (row-major, lower).
  * Replaces torch.linalg.cholesky + L.inverse() (cigp.py:129-131, gp_computation_pack.py:108-109).
  * A [batch][n][n] (only the lower triangle is read); L, Linv [batch][n][n] (either may be NULL).
