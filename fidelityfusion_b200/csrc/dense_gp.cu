@@ -12,6 +12,7 @@
 #include "xgrad_kernels.cuh"
 #include "acq_kernels.cuh"
 #include "train_kernels.cuh"
+#include "match_kernels.cuh"
 
 namespace ffgp {
 
@@ -1004,6 +1005,21 @@ int ffgp_adam_step_f64(void* const* table, const int* sizes, int ntensors, doubl
     return fail(-2, "ffgp_adam_step_f64: bad hyper-parameter");
   adam_step_kernel<<<ntensors, 256, 0, (cudaStream_t)stream>>>(table, sizes, lr, beta1, beta2, eps, maximize, loss, loss_hist,
                                                              loss_hist ? hist_cap : 0);
+  FFGP_LAUNCHED();
+  return 0;
+}
+
+int ffgp_row_match_f64(const double* a, const double* b, int na, int nb, int d, int* match, void* stream) {
+  if (!a || !b || !match) return fail(-1, "ffgp_row_match_f64: null pointer");
+  if (na <= 0 || nb <= 0 || d <= 0) return fail(-2, "ffgp_row_match_f64: bad size");
+  const size_t smem = (size_t)MATCH_ROWS * (2 * d + 1) * sizeof(double);
+  if (smem > 200 * 1024) return fail(-2, "ffgp_row_match_f64: d too large (rows of up to 99 values)");
+  static bool attr = false;
+  if (!attr) {
+    FFGP_CUDA(cudaFuncSetAttribute(row_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  row_match_kernel<<<(na + MATCH_ROWS - 1) / MATCH_ROWS, MATCH_ROWS, smem, (cudaStream_t)stream>>>(a, b, na, nb, d, match);
   FFGP_LAUNCHED();
   return 0;
 }

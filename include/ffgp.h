@@ -171,6 +171,14 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
                        double* out_mean, double* out_cov, int* info, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Subset / overlap matching of two fidelities' inputs: match[i] = smallest j with b[j][:] == a[i][:]
+ * under IEEE equality (NaN matches nothing, -0.0 == 0.0), else -1.  a [na][d], b [nb][d], match int[na].
+ * Replaces the [na][nb][d] broadcast compare of FidelityFusion_Models/MF_data.py:199-202 / 235-238
+ * (get_overlap_input_data / get_unique_input_data) and the unique()-based MFGP_ver2023May/utils/subset_tools.py:58-90.
+ * --------------------------------------------------------------------------------------- */
+int ffgp_row_match_f64(const double* a, const double* b, int na, int nb, int d, int* match, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Device-side optimiser step.  torch.optim.Adam semantics (no weight decay, no amsgrad; operation
  * order of torch/optim/adam.py::_single_tensor_adam) for `ntensors` parameter tensors in ONE launch; replaces the
  * optimizer.step() of the reference's training loops (FidelityFusion_Models/CIGAR.py:96-106, AR_autoRegression.py:

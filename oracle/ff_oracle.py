@@ -399,3 +399,26 @@ def dense_nll_grads_analytic_numpy(x, y, ls_raw, sv_raw, log_beta, eps=1e-9, pi=
     g_sv = W.sum() / amp * np.sign(float(sv_raw))
     g_lb = -noise * np.trace(G)
     return nll, {'length_scales': g_ls, 'signal_variance': g_sv, 'log_beta': g_lb, 'y': alpha}
+
+
+# ---------------------------------------------------------------------------------------------
+# Data-side matching
+# ---------------------------------------------------------------------------------------------
+def overlap_masks(x1, x2):
+    """FidelityFusion_Models/MF_data.py:199-202 (and 235-238 negated): rows of x1 present in x2 and vice versa, by the
+    reference's own [n1, n2, d] broadcast compare."""
+    m1 = torch.all(x1.unsqueeze(1) == x2.unsqueeze(0), dim=-1).any(dim=-1)
+    m2 = torch.all(x2.unsqueeze(1) == x1.unsqueeze(0), dim=-1).any(dim=-1)
+    return m1, m2
+
+
+def get_subset_index(data_a, data_b):
+    """MFGP_ver2023May/utils/subset_tools.py:58-90 with subset_type='index', restated: for every sample shared by a and
+    b (in the order torch.unique(dim=0) lists them) its index in a and its index in b."""
+    na = data_a.shape[0]
+    allr = torch.cat([data_a, data_b], 0)
+    _, inv, cnt = allr.unique(sorted=False, return_inverse=True, return_counts=True, dim=0)
+    rep = torch.arange(len(cnt))[cnt > 1]
+    mask = (inv.reshape(-1, 1) - rep.reshape(1, -1)) == 0
+    idx = torch.arange(mask.shape[0]).reshape(-1, 1) * mask
+    return idx[:na].sum(0), idx[na:].sum(0) - na
