@@ -1,0 +1,68 @@
+"""Residual kernel of FIDES / the continuous autoregression (reference MFGP_ver2023May/kernel/MCMC_res_kernel.py:4-69):
+an SE kernel in x times a SCALAR Monte-Carlo integral over the fidelity variable,
+
+    K = z_part_mc * scale * exp(-0.5 |(X1 - X2) / l|^2),
+    z_part_mc = mean_n exp(-b (z1_n - h1) - b (z2_n - h2) - 0.5 ((z1_n - z2_n) / l_z)^2) * (h1 - l1) (h2 - l2),
+    z1, z2 ~ U[l, h], N = 100 samples drawn after torch.manual_seed(1024) on EVERY evaluation (:47-49; the global RNG
+    side effect is part of the reference's behaviour).
+
+The x part is the fused kernel-matrix assembly (ffgp_kernel_matrix_f64 / the fused NLL); the scalar integral is a
+100-element torch expression whose autograd carries the gradient to `length_scale_z` and `b`.  The samples are drawn
+from the CPU generator (as the reference does when it runs where our oracle can pin it) and moved to the parameters'
+device."""
+import torch
+
+from ... import ops
+
+
+class Kernel_res(torch.nn.Module):
+    def __init__(self, noise_exp_format, length_scale=1., scale=1., length_scale_z=1., const_item=torch.tensor(3.).sqrt()) -> None:
+        super().__init__()
+        # `is True` by identity: a config DICT passed positionally by kernel_utils.create_kernel selects the linear format
+        self.noise_exp_format = noise_exp_format
+        length_scale = torch.tensor(length_scale)
+        scale = torch.tensor(scale)
+        length_scale_z = torch.tensor(length_scale_z)
+        self.const_item = const_item
+        if noise_exp_format is True:
+            self.length_scale = torch.nn.Parameter(torch.log(length_scale))
+            self.scale = torch.nn.Parameter(torch.log(scale))
+            self.length_scale_z = torch.nn.Parameter(torch.log(length_scale_z))
+        else:
+            self.length_scale = torch.nn.Parameter(length_scale)
+            self.scale = torch.nn.Parameter(scale)
+            self.length_scale_z = torch.nn.Parameter(length_scale_z)
+        self.b = torch.nn.Parameter(torch.tensor(1.))
+        self.seed = 1024
+
+    def warp(self, l1, h1, l2, h2):
+        return l1, h1, l2, h2
+
+    def _values(self):
+        if self.noise_exp_format is True:
+            return torch.exp(self.length_scale), torch.exp(self.scale), torch.exp(self.length_scale_z)
+        return self.length_scale, self.scale, self.length_scale_z
+
+    def z_part_mc(self, l1, h1, l2, h2):
+        """MCMC_res_kernel.py:44-64."""
+        _, _, length_scale_z = self._values()
+        lf1, hf1, lf2, hf2 = self.warp(l1, h1, l2, h2)
+        N = 100
+        dev, dt = self.b.device, self.b.dtype
+        torch.manual_seed(self.seed)
+        z1 = (torch.rand(N) * (hf1 - lf1) + lf1).to(device=dev, dtype=dt)
+        z2 = (torch.rand(N) * (hf2 - lf2) + lf2).to(device=dev, dtype=dt)
+        lz = length_scale_z.view(1, -1)
+        dist_z = (z1 / lz - z2 / lz) ** 2
+        z_part = (-self.b * (z1 - hf1) - self.b * (z2 - hf2) - 0.5 * dist_z).exp()
+        return z_part.mean() * (hf1 - lf1) * (hf2 - lf2)
+
+    def fused_params(self, l1, h1, l2, h2):
+        """(inv_ls, amp, clamp) of the stationary SE family the C ABI assembles: amp carries the scalar integral."""
+        length_scale, scale, _ = self._values()
+        amp = (scale.reshape(-1) * self.z_part_mc(l1, h1, l2, h2)).reshape(-1)
+        return (1.0 / length_scale).reshape(-1), amp, False
+
+    def forward(self, X1, X2, l1, h1, l2, h2):
+        inv_ls, amp, clamp = self.fused_params(l1, h1, l2, h2)
+        return ops.kernel_matrix(X1, X2, inv_ls, amp, clamp)

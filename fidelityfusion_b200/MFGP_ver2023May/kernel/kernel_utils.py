@@ -22,4 +22,7 @@ def create_kernel(kernel_config):
     for kernel_name, kernel_config in kernel_config.items():
         if kernel_name == 'SE':
             return SE_kernel(kernel_config)
+        elif kernel_name == 'kernel_res':
+            from .MCMC_res_kernel import Kernel_res
+            return Kernel_res(kernel_config)
         raise NotImplementedError

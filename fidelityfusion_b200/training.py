@@ -26,6 +26,14 @@ from . import _lib as B
 from . import ops
 
 
+def _bump_versions(params):
+    """The kernels write parameter memory behind autograd's back: advance the tensors' version counters, which is
+    what an in-place torch op would have done (ops.state_token keys the resident factorisation on them, and autograd
+    uses them to detect stale saved tensors)."""
+    for p in params:
+        torch.autograd.graph.increment_version(p)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """`torch.optim.Adam(params, lr, betas, eps, maximize=...)` with the update fused into one CUDA launch.
 
@@ -106,6 +114,7 @@ class FusedAdam(torch.optim.Optimizer):
                                       float(group['eps']), int(bool(group['maximize'])), loss_p, hist_p, self._hist_cap,
                                       B.stream_ptr())
             B.check(rc, 'ffgp_adam_step_f64')
+            _bump_versions(active)
             first = False
         return out
 
@@ -188,6 +197,7 @@ class GraphedTrainer:
         for _ in range(int(iterations)):
             self.graph.replay()
         self.steps += int(iterations)
+        _bump_versions(self.active)                # a replay does not run the Python side of FusedAdam.step
         if check:
             self.check()
         return self

@@ -422,3 +422,33 @@ def get_subset_index(data_a, data_b):
     mask = (inv.reshape(-1, 1) - rep.reshape(1, -1)) == 0
     idx = torch.arange(mask.shape[0]).reshape(-1, 1) * mask
     return idx[:na].sum(0), idx[na:].sum(0) - na
+
+
+# ---------------------------------------------------------------------------------------------
+# FIDES residual kernel (a12)
+# ---------------------------------------------------------------------------------------------
+def kernel_res(X1, X2, length_scale, scale, length_scale_z, b, l1, h1, l2, h2, exp_format=False, seed=1024):
+    """MFGP_ver2023May/kernel/MCMC_res_kernel.py:33-69: SE kernel in x times the scalar Monte-Carlo integral over the
+    fidelity variable; reseeds the global RNG on every call (:47).  Parameters are the RAW nn.Parameter values."""
+    if exp_format:
+        length_scale, scale, length_scale_z = torch.exp(length_scale), torch.exp(scale), torch.exp(length_scale_z)
+    length_scale, scale, length_scale_z = length_scale.view(1, -1), scale.view(1, -1), length_scale_z.view(1, -1)
+    N = 100
+    torch.manual_seed(seed)
+    z1 = torch.rand(N) * (h1 - l1) + l1
+    z2 = torch.rand(N) * (h2 - l2) + l2
+    X1 = X1 / length_scale
+    X2 = X2 / length_scale
+    n1 = torch.sum(X1 * X1, dim=1).view(-1, 1)
+    n2 = torch.sum(X2 * X2, dim=1).view(-1, 1)
+    K = -2.0 * X1 @ X2.t() + n1.expand(X1.size(0), X2.size(0)) + n2.t().expand(X1.size(0), X2.size(0))
+    K = scale * torch.exp(-0.5 * K)
+    dist_z = (z1 / length_scale_z - z2 / length_scale_z) ** 2
+    z_part = (-b * (z1 - h1) - b * (z2 - h2) - 0.5 * dist_z).exp()
+    return z_part.mean() * (h1 - l1) * (h2 - l2) * K
+
+
+def FIDES_predict(K, Kx, kxx_diag, noise, y):
+    """base_gp/fides.py:74-109: like CIGP.forward but the variance stays a column [N*, 1]."""
+    u, var = CIGP_predict(K, Kx, kxx_diag, noise, y)
+    return u, var[:, :1]

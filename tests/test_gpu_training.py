@@ -137,3 +137,21 @@ def test_graphed_trainer_on_the_kronecker_model():
     tr = GraphedTrainer(lambda: hg.compute_loss(x, Y), hg.parameters(), lr=0.01, history=8).run(8)
     assert torch.equal(_params(he), _params(hg))
     assert torch.equal(curve_e.cpu(), tr.losses().cpu())
+
+
+def test_prediction_after_graphed_training_uses_the_trained_parameters():
+    """cigp.forward keeps (L^-1, alpha) resident between calls, keyed on the parameters' version counters
+    (ops.state_token); training by graph replay must invalidate it like torch's in-place optimiser update would."""
+    from fidelityfusion_b200.training import GraphedTrainer
+    x, y = _data(90, 2, seed=5)
+    xs = _data(11, 2, seed=6)[0].cuda()
+    xc, yc = x.cuda(), y.cuda()
+    m = _model(2)
+    with torch.no_grad():
+        before = m(xc, yc, xs)[0].clone()
+    GraphedTrainer(lambda: -m.negative_log_likelihood(xc, yc), m.parameters(), lr=0.05).run(10)
+    fresh = _model(2)
+    fresh.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        after, want = m(xc, yc, xs)[0], fresh(xc, yc, xs)[0]
+    assert torch.equal(after, want) and not torch.equal(after, before)
