@@ -83,6 +83,19 @@ static thread_local int g_cta_cap = 0;   // > 0: see gemm()
 // M^T M product (+20 %), so only the former use it.
 // FFGP_PERSIST=0 disables it (A/B comparisons), FFGP_PERSIST=2 forces it for every launch (tests/test_gpu_gemm.py).
 static thread_local int g_persist = 0;
+// > 0: the launch runs as a persistent grid on all SMs but this many, which stay free for the high-priority panel chain
+// of a single large factorisation (see potrf_right_looking).  FFGP_SYRK_RESERVE sets it.
+static thread_local int g_reserve_sms = 0;
+static int persist_lower() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_PERSIST_LOWER"); v = e ? atoi(e) : 0; }
+  return v;
+}
+static int syrk_reserve() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_SYRK_RESERVE"); v = e ? atoi(e) : 0; }
+  return v;
+}
 static int persist_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FFGP_PERSIST"); v = e ? atoi(e) : 1; }
@@ -141,7 +154,9 @@ static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long
     if (tiles < (long long)num_sms()) big = false;     // 64x64 tiles: 4x the CTAs for the small levels
   }
   cudaError_t e = cudaErrorNotSupported;
-  if (big && use_tma_gemm()) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st, (persist_mode() == 2 || (g_persist && persist_mode() == 1 && beta == 0.0 && !lower_only)) ? num_sms() : 0);
+  int persistent_ctas = (persist_mode() == 2 || (g_persist && persist_mode() == 1 && (!lower_only || persist_lower()))) ? num_sms() : 0;
+  if (g_reserve_sms > 0 && g_reserve_sms < num_sms()) persistent_ctas = num_sms() - g_reserve_sms;
+  if (big && use_tma_gemm()) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st, persistent_ctas);
   if (e == cudaErrorNotSupported) {
     if (a_kmaj && b_kmaj) e = launch_gemm<true, true>(p, batch, big, st);
     else if (a_kmaj && !b_kmaj) e = launch_gemm<true, false>(p, batch, big, st);
@@ -383,8 +398,11 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
         return e;
       // (c) rest of the trailing update of step k (independent of the panel): lower tiles of A[k+2:, k+2:]
       g_trace_label = "c:syrk";
-      if ((e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 2, k), c.ld, c.sb, c.A + at(k + 2, k + 2), c.ld,
-                    c.sb, rows2, rows2, NB, -1.0, 1.0, 1, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+      if (aux) g_reserve_sms = syrk_reserve();
+      e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 2, k), c.ld, c.sb, c.A + at(k + 2, k + 2), c.ld,
+               c.sb, rows2, rows2, NB, -1.0, 1.0, 1, K_FULL, c.batch, c.st);
+      g_reserve_sms = 0;
+      if (e != cudaSuccess) return e;
     }
     if (aux) {
       if ((e = cudaEventRecord(aux->ev_aux, aux->st)) != cudaSuccess) return e;

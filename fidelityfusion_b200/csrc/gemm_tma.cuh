@@ -45,6 +45,7 @@ struct TmaGemmParams {
   int M, N, K, inner;
   double alpha, beta;
   int lower_only, kmode, heavy_first;
+  int zero;                  // always 0 (a run-time value the compiler cannot fold, see the stage release)
   int tiles, total;          // tiles per problem, work items of the launch (tiles x problems); grid.x <= total
   unsigned int* sched;       // NULL: one work item per CTA (grid.x == total).  Else {next, done} counters, both zero at
                              // launch and reset by the last CTA: CTAs fetch further work items as they finish
@@ -224,9 +225,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   };
 
   const double alpha = p.alpha, beta = p.beta;
-  // one tile per CTA: beta C enters through the accumulators (read overlapped with the first panel loads); persistent
-  // grid: through the epilogue
-  const bool init_from_c = (beta != 0.0) && (alpha != 0.0) && !p.sched;
+  // beta C enters through the accumulators: the tile of C is read while the first panels are in flight
+  const bool init_from_c = (beta != 0.0) && (alpha != 0.0);
   const int role = wm * 4 + wn;
   double acc[MT][NT][2];
   int it0 = 0;                                     // k-steps consumed before this tile (the stage ring runs on across tiles)
@@ -282,6 +282,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     using Lv = decltype(lv);
     const int s = (it0 + kt) % TG_STAGES;
     const uint32_t stage_base = smem_base + s * TG_STAGE_BYTES;
+    uint32_t rel = 0;
 #pragma unroll
     for (int kk = 0; kk < TG_BK / 4; kk++) {
       const int cur = kk & 1, nxt = cur ^ 1;
@@ -297,10 +298,26 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < NT; j++)
           if (Lv::live(i, j)) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+      // Stage release.  An mbarrier arrive does not wait for the warp's outstanding ld.shared, and ptxas is free to
+      // sink fragment loads and hoist the arrive, so "arrive after the loads were issued" is a race with the TMA refill
+      // of the stage (generic-proxy reads vs async-proxy writes).  It showed once the ring stayed full and the
+      // load/store queue was backed up (persistent grid + 64 global loads of C per thread at the start of a tile): one
+      // warp's last-loaded A / B fragments were overwritten before they were served, ~1 tile in 500 wrong
+      // (tools/diag_initc.py).  So the barrier ADDRESS is made data-dependent on EVERY fragment read from this stage:
+      // `rel` ORs the low words of the fragments after the DMMAs that consumed them (no extra wait: the registers are
+      // ready by then) plus, at the release point, the ones just requested for the last k4 step; `& p.zero` (a run-time
+      // zero) keeps the chain alive through ptxas.  The arrive cannot issue before all those loads have returned.
+#pragma unroll
+      for (int i = 0; i < MT; i++) rel |= (uint32_t)__double2loint(af[cur][i]);
+#pragma unroll
+      for (int j = 0; j < NT; j++) rel |= (uint32_t)__double2loint(bf[cur][j]);
       if (kk == TG_BK / 4 - 2) {
-        // the last fragments of this stage are in registers: hand the stage back to the producer
+#pragma unroll
+        for (int i = 0; i < MT; i++) rel |= (uint32_t)__double2loint(af[nxt][i]);
+#pragma unroll
+        for (int j = 0; j < NT; j++) rel |= (uint32_t)__double2loint(bf[nxt][j]);
         __syncwarp();
-        if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s);
+        if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s + (rel & (uint32_t)p.zero));
       }
     }
   };
@@ -369,7 +386,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const int col = j0 + (4 * j + wn) * 8 + tq * 2;
       double2* dst = reinterpret_cast<double2*>(Cg + (long long)row * p.ldc + col);
       double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
-      if (beta != 0.0 && !init_from_c) {        // the 64 loads of a thread are independent: one memory latency per tile
+      if (beta != 0.0 && !init_from_c) {        // alpha == 0: C is only scaled
         const double2 o = *dst;
         v.x = fma(beta, o.x, v.x);
         v.y = fma(beta, o.y, v.y);
@@ -478,7 +495,7 @@ inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p
   const int tiles = p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   const long long total = (long long)tiles * batch_outer * p.inner;
   if (total > 0x7fffffffLL) return cudaErrorNotSupported;
-  tp.tiles = tiles; tp.total = (int)total;
+  tp.tiles = tiles; tp.total = (int)total; tp.zero = 0;
   int grid = (int)total;
   tp.sched = nullptr;
   if (persistent_ctas > 0 && total > persistent_ctas) {
