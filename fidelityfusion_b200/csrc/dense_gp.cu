@@ -91,6 +91,16 @@ static int persist_lower() {
   if (v < 0) { const char* e = getenv("FFGP_PERSIST_LOWER"); v = e ? atoi(e) : 0; }
   return v;
 }
+static int sched_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_SCHED"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static int split_colupd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_SPLIT_COLUPD"); v = e ? atoi(e) : 0; }
+  return v;
+}
 static int syrk_reserve() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FFGP_SYRK_RESERVE"); v = e ? atoi(e) : 0; }
@@ -311,7 +321,7 @@ struct AuxStream {
   cudaStream_t st = nullptr;        // panel chain (highest priority)
   cudaStream_t st_bulk = nullptr;   // trailing updates of a large single factorisation (middle priority)
   cudaStream_t st_bg = nullptr;     // background work overlapped with the chain-bound tail (lowest priority)
-  cudaEvent_t ev_main = nullptr, ev_aux = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_half = nullptr, ev_bg = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_aux = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_half = nullptr, ev_bg = nullptr, ev_rest = nullptr;
 };
 static AuxStream g_aux[64];
 
@@ -326,7 +336,7 @@ static cudaError_t get_aux(AuxStream** out) {
     if ((e = cudaStreamCreateWithPriority(&a.st, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithPriority(&a.st_bulk, cudaStreamNonBlocking, (lo + hi) / 2)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithPriority(&a.st_bg, cudaStreamNonBlocking, lo)) != cudaSuccess) return e;
-    cudaEvent_t* evs[6] = {&a.ev_main, &a.ev_aux, &a.ev_fork, &a.ev_join, &a.ev_half, &a.ev_bg};
+    cudaEvent_t* evs[7] = {&a.ev_main, &a.ev_aux, &a.ev_fork, &a.ev_join, &a.ev_half, &a.ev_bg, &a.ev_rest};
     for (auto ev : evs)
       if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
   }
@@ -370,6 +380,7 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
   for (int k = 0; k + 1 < nblk; k++) {
     const int rows1 = np - (k + 1) * NB;            // rows below block row k
     // (a) rank-NB update of block column k+1
+    bool chain_released = false;
     g_trace_label = "a:colupd";
     if (!lookahead) {
       // batched problems (no panel chain to protect): the NB x NB diagonal block of the column is symmetric - lower
@@ -379,23 +390,47 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
       if (rows1 > NB &&
           (e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 2, k + 1), c.ld,
                     c.sb, rows1 - NB, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
-    } else if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1),
-                         c.ld, c.sb, rows1, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+    } else {
+      // look-ahead: the diagonal block of the column first - it is all the panel chain needs - then the rows below it,
+      // which only the TRSM of the panel needs.  FFGP_SPLIT_COLUPD=1 enables it; measured at N = 8192: 20.9-21.6 ms/eval
+      // against 20.6 with the single launch (the chain is not what bounds a step, profiles/r01_c2_schedule_experiments.txt)
+      const int rows_first = (aux && split_colupd() && rows1 > NB) ? NB : rows1;
+      if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1),
+                    c.ld, c.sb, rows_first, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+      if (rows_first < rows1) {
+        if ((e = cudaEventRecord(aux->ev_main, c.st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(aux->st, aux->ev_main, 0)) != cudaSuccess) return e;
+        chain_released = true;
+        if ((e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 2, k + 1),
+                      c.ld, c.sb, rows1 - NB, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(aux->ev_rest, c.st)) != cudaSuccess) return e;
+      }
+    }
     cudaStream_t ps = c.st;
     if (aux) {
-      if ((e = cudaEventRecord(aux->ev_main, c.st)) != cudaSuccess) return e;
-      if ((e = cudaStreamWaitEvent(aux->st, aux->ev_main, 0)) != cudaSuccess) return e;
+      if (!chain_released) {
+        if ((e = cudaEventRecord(aux->ev_main, c.st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(aux->st, aux->ev_main, 0)) != cudaSuccess) return e;
+      }
       ps = aux->st;
     }
     // (b) panel k+1: diagonal block (factor + inverse), then TRSM of the rows below it
     g_trace_label = "b:panel";
     if ((e = factor_rec(aux ? ca : c, (k + 1) * NB, NB)) != cudaSuccess) return e;
     const int rows2 = np - (k + 2) * NB;
+    // Schedule 2 (FFGP_SCHED=2, experiment): the trailing update runs as a persistent grid that leaves FFGP_SYRK_RESERVE
+    // SMs to the diagonal-block chain on the side stream, and the TRSM of the panel follows it on the MAIN stream (all
+    // SMs).  The chain shrinks from ~200 to ~140 us per block but a step is bound by SYRK + TRSM + column update:
+    // no gain at N = 8192 (profiles/r01_c2_schedule_experiments.txt), so the default stays schedule 1.
+    const bool sched2 = aux && sched_mode() == 2;
     if (rows2 > 0) {
-      g_trace_label = "b:trsm";
-      if ((e = gemm(true, true, c.A + at(k + 2, k + 1), c.ld, c.sb, c.M + at(k + 1, k + 1), c.ld, c.sb,
-                    c.L + at(k + 2, k + 1), c.ld, c.sb, rows2, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, ps)) != cudaSuccess)
-        return e;
+      if (!sched2) {
+        g_trace_label = "b:trsm";
+        if (chain_released && (e = cudaStreamWaitEvent(ps, aux->ev_rest, 0)) != cudaSuccess) return e;
+        if ((e = gemm(true, true, c.A + at(k + 2, k + 1), c.ld, c.sb, c.M + at(k + 1, k + 1), c.ld, c.sb,
+                      c.L + at(k + 2, k + 1), c.ld, c.sb, rows2, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, ps)) != cudaSuccess)
+          return e;
+      }
       // (c) rest of the trailing update of step k (independent of the panel): lower tiles of A[k+2:, k+2:]
       g_trace_label = "c:syrk";
       if (aux) g_reserve_sms = syrk_reserve();
@@ -407,6 +442,12 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
     if (aux) {
       if ((e = cudaEventRecord(aux->ev_aux, aux->st)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(c.st, aux->ev_aux, 0)) != cudaSuccess) return e;
+    }
+    if (sched2 && rows2 > 0) {
+      g_trace_label = "b:trsm";
+      if ((e = gemm(true, true, c.A + at(k + 2, k + 1), c.ld, c.sb, c.M + at(k + 1, k + 1), c.ld, c.sb,
+                    c.L + at(k + 2, k + 1), c.ld, c.sb, rows2, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, c.st)) != cudaSuccess)
+        return e;
     }
     if ((k + 2) * 2 == nblk && (e = at_half()) != cudaSuccess) return e;
   }

@@ -303,7 +303,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // of the stage (generic-proxy reads vs async-proxy writes).  It showed once the ring stayed full and the
       // load/store queue was backed up (persistent grid + 64 global loads of C per thread at the start of a tile): one
       // warp's last-loaded A / B fragments were overwritten before they were served, ~1 tile in 500 wrong
-      // (tools/diag_initc.py).  So the barrier ADDRESS is made data-dependent on EVERY fragment read from this stage:
+      // (tools/diag_stage_release.py).  So the barrier ADDRESS is made data-dependent on EVERY fragment read from this stage:
       // `rel` ORs the low words of the fragments after the DMMAs that consumed them (no extra wait: the registers are
       // ready by then) plus, at the release point, the ones just requested for the last k4 step; `& p.zero` (a run-time
       // zero) keeps the chain alive through ptxas.  The arrive cannot issue before all those loads have returned.

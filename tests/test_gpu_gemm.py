@@ -13,6 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize('persist', ['0', '2'])
 def test_gemm_all_modes(persist):
     env = dict(os.environ, FFGP_PERSIST=persist)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'check_gemm.py')], env=env, capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    # the persistent grid is run three times: the stage-release race it once exposed hit ~1 tile in 500 (gemm_tma.cuh)
+    for _ in range(3 if persist == '2' else 1):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'check_gemm.py')], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]

@@ -1,3 +1,8 @@
+"""Stress of the TMA GEMM stage release (persistent grid, beta != 0: C is read at the start of every tile, which backs up
+the load/store queue while the ring is full).  Reports tiles whose result differs from torch and, for those, which 8x8
+fragments of which warp are wrong.  History: with the stage released right after ISSUING the last fragment loads, ~1 tile
+in 500 came out wrong in one warp's last-loaded A / B fragments (see gemm_tma.cuh, "Stage release").
+   FFGP_PERSIST=2 python tools/diag_stage_release.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
