@@ -23,13 +23,18 @@ PI = 3.1415
 EPS = 1e-9
 
 
-def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True):
+def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True, check=True):
     """x [B,n,d], y [B,n,D], length_scales [B,d], signal_variance [B], log_beta [B] (raw reference parameters),
     xs [B,ns,d] or None.  Returns dict: nll [B] (= -cigp.negative_log_likelihood), g_length_scales [B,d],
     g_signal_variance [B], g_log_beta [B], and mean [B,ns,D], var [B,ns] (diag of cigp.forward's covariance).
 
     ONE C call (ffgp_dense_fit_f64): every problem is factorised once and the NLL, its analytic gradient and the
-    posterior all come from that factor; the chain rule to the reference's raw parameters is a few vector ops."""
+    posterior all come from that factor; the chain rule to the reference's raw parameters is a few vector ops.
+
+    check=True raises torch.linalg.LinAlgError at the call when a covariance is not positive definite, like the
+    reference's torch.linalg.cholesky - which costs a host synchronisation per call.  check=False keeps the call
+    asynchronous (sweeps can be enqueued back to back) and returns the LAPACK-style status as out['info'] (fp64 [B],
+    0 = ok, k = leading minor k not PD) for the caller to inspect, e.g. once per optimisation step: `check_batch_info`."""
     from . import _lib as B
     L = B.lib()
     Bn, n, d = x.shape
@@ -61,8 +66,11 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
                               B.ptr(nll), None, B.ptr(alpha), B.ptr(g_il), B.ptr(g_amp), B.ptr(g_diag), None,
                               B.ptr(mean), B.ptr(var), B.ptr(info), B.stream_ptr())
     B.check(rc, 'ffgp_dense_fit_f64')
-    ops.check_info(info)
+    if check:
+        ops.check_info(info)
     out = {'nll': nll + 0.5 * n * D * math.log(2 * PI)}
+    if not check:
+        out['info'] = info.to(torch.float64)
     if want_grad:
         out['g_length_scales'] = g_il * (-1.0 / (ell * ell)) * torch.sign(ls)       # inv_ls = 1/(|ls|+eps)
         out['g_signal_variance'] = g_amp * torch.sign(sv)                           # amp = |sv|
@@ -71,6 +79,12 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
         out['mean'] = mean
         out['var'] = var
     return out
+
+
+def check_batch_info(info):
+    """Raise what the reference raises for the first problem whose covariance was not positive definite
+    (`info` = out['info'] of a check=False evaluation, possibly all-gathered over the ranks).  One host sync."""
+    ops.check_info(info.round().to(torch.int32))
 
 
 def shard_range(total, rank, world):
@@ -95,20 +109,21 @@ def unpack_results(buf, shapes, keys):
 
 
 def sharded_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True, group=None,
-                      compute_fn=batched_cigp_eval):
+                      compute_fn=batched_cigp_eval, check=True):
     """Every rank passes the FULL problem set (or at least its own block - only [lo,hi) is read) and receives the
     full result set.  Falls back to a single-rank call when torch.distributed is not initialised.
     `compute_fn` exists so the CPU (gloo) tests can exercise the partition/gather logic without a GPU."""
     import torch.distributed as dist
+    kw = {} if check else {'check': False}
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return compute_fn(x, y, length_scales, signal_variance, log_beta, xs, want_grad)
+        return compute_fn(x, y, length_scales, signal_variance, log_beta, xs, want_grad, **kw)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     Bn = x.shape[0]
     lo, hi = shard_range(Bn, rank, world)
     sl = slice(lo, hi)
     res = compute_fn(x[sl], y[sl], length_scales[sl], signal_variance[sl], log_beta[sl],
-                     None if xs is None else xs[sl], want_grad)
-    keys = [k for k in ('nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var') if k in res]
+                     None if xs is None else xs[sl], want_grad, **kw)
+    keys = [k for k in ('nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var', 'info') if k in res]
     shapes = {k: tuple(res[k].shape[1:]) for k in keys}
     local = pack_results(res, keys)
     counts = [shard_range(Bn, r, world) for r in range(world)]

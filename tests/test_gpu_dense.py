@@ -264,6 +264,33 @@ def test_c5_batched_independent_gps():
         assert rel_err(out['var'][b].cpu(), g[f'vdiag{b}']) < TOL
 
 
+def test_batched_eval_asynchronous_status():
+    """check=False: no host sync inside the call, the LAPACK-style status comes back with the results; the values are
+    those of the checked call, and a non-PD problem (NaN noise) is reported for its batch index either way."""
+    from fidelityfusion_b200.batched import batched_cigp_eval, check_batch_info
+    gen = torch.Generator().manual_seed(77)
+    Bn, n, d, ns = 9, 200, 3, 5
+    x = torch.rand(Bn, n, d, generator=gen).to(DEV)
+    y = torch.randn(Bn, n, 1, generator=gen).to(DEV)
+    xs = torch.rand(Bn, ns, d, generator=gen).to(DEV)
+    ls, sv, lb = torch.ones(Bn, d, device=DEV), torch.ones(Bn, device=DEV), torch.ones(Bn, device=DEV)
+    a = batched_cigp_eval(x, y, ls, sv, lb, xs)
+    b = batched_cigp_eval(x, y, ls, sv, lb, xs, check=False)
+    assert 'info' not in a and float(b['info'].abs().sum()) == 0.0
+    check_batch_info(b['info'])
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    lb_bad = lb.clone()
+    lb_bad[3] = float('nan')
+    with pytest.raises(torch.linalg.LinAlgError, match='Batch element 3'):
+        batched_cigp_eval(x, y, ls, sv, lb_bad, xs)
+    c = batched_cigp_eval(x, y, ls, sv, lb_bad, xs, check=False)
+    assert float(c['info'][3]) > 0 and float(c['info'].abs().sum()) == float(c['info'][3])
+    with pytest.raises(torch.linalg.LinAlgError, match='Batch element 3'):
+        check_batch_info(c['info'])
+    assert torch.equal(c['nll'][:3], a['nll'][:3]) and torch.equal(c['nll'][4:], a['nll'][4:])
+
+
 def test_c5_full_size_batch_vs_oracle_subset():
     """C5 recipe at N=512, d=8: 256 problems in one call, 8 of them checked against the oracle."""
     from fidelityfusion_b200.batched import batched_cigp_eval
