@@ -846,6 +846,9 @@ syevj_cluster_kernel(const double* __restrict__ Ain, int n, double* __restrict__
   const uint32_t r_flag = dsmem_addr(flag, 1), r_perm = dsmem_addr(perm, 1);
   cluster_sync_all();                                  // both CTAs resident and initialised before any DSMEM store
 
+  // loop-invariant thread -> work maps (see the update loops)
+  const int k2u = tid % half, k1s = (tid < (SC_THREADS / half) * half) ? tid / half : half, k1step = SC_THREADS / half;
+  const int vj = tid % n, vks = (tid < (SC_THREADS / n) * n) ? tid / n : half, vkstep = SC_THREADS / n;
   int converged = 0;
   if (rank == 0 && norm2 == 0.0) converged = 1;
   // a zero matrix converges immediately; publish that like any sweep result so that both CTAs agree
@@ -877,25 +880,29 @@ syevj_cluster_kernel(const double* __restrict__ Ain, int n, double* __restrict__
       cluster_sync_all();
       if (rank == 0) {
         // fused two-sided update: block (k1, k2) = rows (a1, b1) x columns (a2, b2):  X' = G1 X G2^T, G = [[c, -s], [s, c]]
-        for (int e = tid; e < half * half; e += SC_THREADS) {
-          const int k1 = e / half, k2 = e - k1 * half;
-          const double s1 = rs[bo + k1], s2 = rs[bo + k2];
+        // thread = (column pair k2 fixed, row pairs k1s, k1s + k1step, ..): no index division in the loop and the column
+        // pair's rotation is loaded once per step
+        if (k1s < half) {
+         const double s2 = rs[bo + k2u], c2 = rc[bo + k2u];
+         const int ca = ra[bo + k2u], cb = rb[bo + k2u];
+         for (int k1 = k1s; k1 < half; k1 += k1step) {
+          const double s1 = rs[bo + k1];
           if (s1 != 0.0 || s2 != 0.0) {
-            const double c1 = rc[bo + k1], c2 = rc[bo + k2];
+            const double c1 = rc[bo + k1];
             double* r0 = mat + ra[bo + k1] * lda;
             double* r1 = mat + rb[bo + k1] * lda;
-            const int ca = ra[bo + k2], cb = rb[bo + k2];
             const double x00 = r0[ca], x01 = r0[cb], x10 = r1[ca], x11 = r1[cb];
             const double y00 = c1 * x00 - s1 * x10, y01 = c1 * x01 - s1 * x11;
             const double y10 = s1 * x00 + c1 * x10, y11 = s1 * x01 + c1 * x11;
             r0[ca] = c2 * y00 - s2 * y01; r0[cb] = s2 * y00 + c2 * y01;
             r1[ca] = c2 * y10 - s2 * y11; r1[cb] = s2 * y10 + c2 * y11;
           }
+         }
         }
         __syncthreads();
       } else {
-        for (int e = tid; e < half * n; e += SC_THREADS) {
-          const int k = e / n, j = e - k * n;
+        for (int k = vks; k < half; k += vkstep) {
+          const int j = vj;
           const double s = rs[bo + k];
           if (s != 0.0) {
             const double c = rc[bo + k];
