@@ -101,6 +101,12 @@ static int split_colupd() {
   if (v < 0) { const char* e = getenv("FFGP_SPLIT_COLUPD"); v = e ? atoi(e) : 0; }
   return v;
 }
+// FFGP_BASE64=1: batched problems bottom out at 64-blocks (experiment, see factor_rec)
+static int batched_base64() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_BASE64"); v = e ? atoi(e) : 0; }
+  return v;
+}
 static int syrk_reserve() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FFGP_SYRK_RESERVE"); v = e ? atoi(e) : 0; }
@@ -204,7 +210,7 @@ static DenseWs layout_ws(int n, int d, int D, int ns, int batch, char* base) {
   w.gemm_rhs = D > 8;
   w.Dp = round_up(std::max(D, 1), 64);
   w.nsp = ns > 0 ? round_up(ns, 64) : 0;
-  w.nblk = w.np / 128;
+  w.nblk = w.np / BASE_N_BATCHED;
   const int gt = w.np / GRAD_T;
   w.ngtile = gt * (gt + 1) / 2;
   const int Dw = w.gemm_rhs ? w.Dp : D;
@@ -269,23 +275,33 @@ struct FactorCtx {
   int ld;
   long long sb;           // batch stride (elements)
   int batch;
-  double* logdet_part; int nblk;
+  double* logdet_part; int nblk;   // partial log-determinants, one slot per BASE_N_BATCHED rows
   int* info;
   cudaStream_t st;
+  int base_n = BASE_N;             // block handled by the base kernel: BASE_N, or BASE_N_BATCHED for batched problems
 };
 
 static cudaError_t factor_rec(const FactorCtx& c, int off, int n) {
   cudaError_t e;
   const long long d0 = (long long)off * c.ld + off;
-  if (n == BASE_N) {
-    potrf_trtri_base_kernel<<<c.batch, 256, BASE_SMEM, c.st>>>(c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part,
-                                                               c.nblk, off / BASE_N, c.info, off);
+  if (n == c.base_n) {
+    // FFGP_BASE64=1 (experiment): batched problems bottom out at 64 instead of 128 - 35 KB of shared memory, two CTAs
+    // per SM, the extra level of 64-wide products through the GEMM kernel.  Measured on 512 x (N = 512)
+    // (profiles/r01_launches_c5_v11_base64.txt): the base kernels drop from 0.76 to 0.45 ms per chunk, but a 64-block
+    // still costs 8 panels x ~3.5 us (the dependent pivot chain and the barriers, not the flops, set the panel time)
+    // and the 16 extra GEMM launches add 0.29 ms: no net gain, so the default stays 128.
+    if (c.base_n == BASE_N)
+      potrf_trtri_base_kernel<BASE_N><<<c.batch, 256, base_smem_bytes(BASE_N), c.st>>>(
+          c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part, c.nblk, off / BASE_N_BATCHED, c.info, off);
+    else
+      potrf_trtri_base_kernel<BASE_N_BATCHED><<<c.batch, 256, base_smem_bytes(BASE_N_BATCHED), c.st>>>(
+          c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part, c.nblk, off / BASE_N_BATCHED, c.info, off);
     ++g_launches;
     trace_mark("base", off, 0, c.st);
     return cudaGetLastError();
   }
-  // split at a multiple of 128: top half gets the larger power-of-two-ish share
-  int h = ((n / BASE_N) + 1) / 2 * BASE_N;
+  // split at a multiple of the base block: top half gets the larger power-of-two-ish share
+  int h = ((n / c.base_n) + 1) / 2 * c.base_n;
   const int m = n - h;
   if ((e = factor_rec(c, off, h)) != cudaSuccess) return e;
   const long long o21 = (long long)(off + h) * c.ld + off;
@@ -584,7 +600,9 @@ static int debug_stop_after() {
 static bool g_attr_done = false;
 static cudaError_t ensure_attrs() {
   if (g_attr_done) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(potrf_trtri_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N_BATCHED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   for (auto kern : {grad_contract_kernel<false>, grad_contract_kernel<true>}) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem_doubles(GRAD_DMAX) * 8);
@@ -626,6 +644,9 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   kernel_matrix_kernel<<<dim3(w.np / 64, w.np / 64, nb), 256, 0, st>>>(kp);
   FFGP_LAUNCHED();
   FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};
+  c.base_n = (nb >= 8 && batched_base64()) ? BASE_N_BATCHED : BASE_N;
+  // one log-det slot per 64 rows; with 128-blocks only every other slot is written
+  FFGP_CUDA(cudaMemsetAsync(w.logdet_part, 0, sizeof(double) * (size_t)nb * w.nblk, st));
   // look-ahead needs spare SMs: with a large batch every launch already fills the machine
   if (nb < 8) {
     bool done = false;

@@ -190,10 +190,11 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixPa
 // warps 1-7 wait before the update).  All loads are unconditional with selected addresses and all masked stores go
 // to a dummy word: no divergent branches in the loop.
 // ------------------------------------------------------------------------------------------
-constexpr int BASE_N = 128;
-constexpr int BASE_LD = 129;
+constexpr int BASE_N = 128;                                  // block size of the single-problem path (and of the padding)
+constexpr int BASE_N_BATCHED = 64;                           // experimental batched base block (see factor_rec); also the log-det slot size
 constexpr int BASE_F = 48;                                   // 36 factor entries + 8 inverses + fail column (+pad)
-constexpr size_t BASE_SMEM = ((size_t)BASE_N * BASE_LD + 2 * BASE_F + 64 + 64 + 8) * sizeof(double);
+constexpr size_t base_smem_bytes(int bn) { return ((size_t)bn * (bn + 1) + 2 * BASE_F + 64 + 64 + 8) * sizeof(double); }
+constexpr size_t BASE_SMEM = base_smem_bytes(BASE_N);
 
 #ifdef FFGP_BASE_TRACE
 __device__ long long g_base_trace[8 * 16 * 4];          // [warp][panel][slot] clock64 stamps (tools/base_trace.cu)
@@ -229,11 +230,14 @@ __device__ __forceinline__ int chol8_regs(double (&l)[8][8], double (&inv)[8]) {
 __device__ __forceinline__ void base_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void base_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
+template <int BN>
+__global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel(
     const double* __restrict__ A, double* __restrict__ L, double* __restrict__ M, int ld, long long sbatch,
     double* __restrict__ logdet_part, int logdet_stride, int blk, int* __restrict__ info, int row_offset) {
+  constexpr int BASE_N = BN, BASE_LD = BN + 1, QV = BN / 32;       // QV: 32-wide groups of virtual columns per lane
+  static_assert(BN == 64 || BN == 128, "base block is 64 or 128");
   extern __shared__ __align__(16) double sm[];
-  double* T = sm;                                   // [128][129]
+  double* T = sm;                                   // [BN][BN + 1]
   double* F = sm + BASE_N * BASE_LD;                // [2][BASE_F] published diagonal factors (double-buffered)
   double* Dn = F + 2 * BASE_F;                      // [36] updated next diagonal block (warp 0 scratch)
   double* red = Dn + 64;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
   // block load: every element is an independent 8-byte cp.async (all in flight at once; a plain load loop
   // serialises 64 global-memory latencies per thread on the single resident CTA)
   for (int e = tid; e < BASE_N * BASE_N; e += 256) {
-    const int i = e >> 7, k = e & 127;
+    const int i = e / BASE_N, k = e % BASE_N;
     if (k <= i) {
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&TT(i, k));
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(A + (long long)i * ld + k));
@@ -418,9 +422,9 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
     BASE_STAMP(p, 1);
     // ---- O.2: rank-8 update of the rows below the panel.  Lane owns virtual columns v = lane + 32 q. ----
     const int nquad = (BASE_N - r0) >> 2;
-    double bv[8][4];
+    double bv[8][QV];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < QV; q++) {
       const int v = lane + 32 * q;
       const int isR = (v < r0) ? 1 : 0;            // running inverse (row block of the panel) vs panel rows of L
       const double* src = T + v * BASE_LD + j0 + isR;
@@ -433,10 +437,10 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
     BASE_STAMP(p, 2);
     for (int rq = warp - 1; rq < nquad; rq += 7) {
       const int i0 = r0 + 4 * rq;
-      double cacc[4][4];
-      int idx[4][4];
+      double cacc[4][QV];
+      int idx[4][QV];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
+      for (int q = 0; q < QV; q++) {
         const int v = lane + 32 * q;
         const bool isR = v < r0;
 #pragma unroll
@@ -456,10 +460,10 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int q = 0; q < 4; q++) cacc[a][q] = fma(av[a], bv[kk][q], cacc[a][q]);
+          for (int q = 0; q < QV; q++) cacc[a][q] = fma(av[a], bv[kk][q], cacc[a][q]);
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < QV; q++)
 #pragma unroll
         for (int a = 0; a < 4; a++) T[idx[a][q]] = cacc[a][q];
     }
@@ -467,12 +471,12 @@ __global__ void __launch_bounds__(256) potrf_trtri_base_kernel(
   }
   __syncthreads();
   for (int e = tid; e < BASE_N * BASE_N; e += 256) {
-    const int i = e >> 7, k = e & 127;
+    const int i = e / BASE_N, k = e % BASE_N;
     L[(long long)i * ld + k] = (k <= i) ? TT(i, k) : 0.0;
     M[(long long)i * ld + k] = (k <= i) ? TT(k, i + 1) : 0.0;
   }
   // sum of log L_ii of this block, fixed order
-  if (tid < 64) red[tid] = log(TT(tid, tid)) + log(TT(tid + 64, tid + 64));
+  if (tid < 64) red[tid] = log(TT(tid, tid)) + (BN == 128 ? log(TT(tid + BN / 2, tid + BN / 2)) : 0.0);
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;

@@ -12,11 +12,11 @@ int main() {
   double *A, *L, *M, *ld; int* info;
   cudaMalloc(&A, n * n * 8); cudaMalloc(&L, n * n * 8); cudaMalloc(&M, n * n * 8); cudaMalloc(&ld, 64); cudaMalloc(&info, 4);
   cudaMemcpy(A, h.data(), n * n * 8, cudaMemcpyHostToDevice); cudaMemset(info, 0, 4);
-  cudaFuncSetAttribute(potrf_trtri_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
-  for (int it = 0; it < 3; it++) potrf_trtri_base_kernel<<<1, 256, BASE_SMEM>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
+  cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
+  for (int it = 0; it < 3; it++) potrf_trtri_base_kernel<BASE_N><<<1, 256, BASE_SMEM>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  for (int it = 0; it < 10; it++) potrf_trtri_base_kernel<<<1, 256, BASE_SMEM>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
+  for (int it = 0; it < 10; it++) potrf_trtri_base_kernel<BASE_N><<<1, 256, BASE_SMEM>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("base kernel: %.2f us per launch (%s)\n", ms * 100, cudaGetErrorString(cudaGetLastError()));
