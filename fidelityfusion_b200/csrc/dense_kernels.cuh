@@ -205,26 +205,38 @@ __device__ long long g_base_trace[8 * 16 * 4];          // [warp][panel][slot] c
 
 // Cholesky of an 8x8 block held in registers (lower part of l), returns first failing column or -1.
 __device__ __forceinline__ int chol8_regs(double (&l)[8][8], double (&inv)[8]) {
+  // Right-looking (outer-product) order: as soon as column c is scaled, its rank-1 update is applied to the columns to
+  // its right.  Every entry still receives its updates in the order k = 0, 1, .. (bitwise the same result as the
+  // dot-product form), but the dependent chain per column shrinks from (2 c + 13) to ~14 FP64 operations - this routine
+  // IS the critical path of a late panel (profiles/r01_base_kernel_timeline_v2.txt: 2100 of ~2900 clk).
   int fail = -1;
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    double s = l[c][c];
-#pragma unroll
-    for (int k = 0; k < c; k++) s = fma(-l[c][k], l[c][k], s);
+    const double s = l[c][c];
     if (!(s > 0.0) && fail < 0) fail = c;
     // one rsqrt replaces sqrt + division on the serial chain (l_cc = s * rsqrt(s), 1/l_cc = rsqrt(s))
     const double rs = rsqrt(s);
     inv[c] = rs;
     l[c][c] = s * rs;
 #pragma unroll
-    for (int r = c + 1; r < 8; r++) {
-      double v = l[r][c];
+    for (int r = c + 1; r < 8; r++) l[r][c] *= rs;
 #pragma unroll
-      for (int k = 0; k < c; k++) v = fma(-l[r][k], l[c][k], v);
-      l[r][c] = v * rs;
-    }
+    for (int r = c + 1; r < 8; r++)
+#pragma unroll
+      for (int k = c + 1; k <= r; k++) l[r][k] = fma(-l[r][c], l[k][c], l[r][k]);
   }
   return fail;
+}
+
+// a <- a L^-T for one row a[0..7] against the 8x8 factor (l, inv): right-looking order, same rounding as the
+// dot-product form, dependent chain 2 operations per column instead of c + 1
+__device__ __forceinline__ void solve8_row(double (&a)[8], const double (&l)[8][8], const double (&inv)[8]) {
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    a[c] *= inv[c];
+#pragma unroll
+    for (int k = c + 1; k < 8; k++) a[k] = fma(-a[c], l[k][c], a[k]);
+  }
 }
 
 __device__ __forceinline__ void base_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -313,13 +325,7 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
         double a[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) a[c] = TT(r, j0 + c);
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          double v = a[c];
-#pragma unroll
-          for (int k = 0; k < c; k++) v = fma(-a[k], l[c][k], v);
-          a[c] = v * inv[c];
-        }
+        solve8_row(a, l, inv);
 #pragma unroll
         for (int c = 0; c < 8; c++) TT(r, j0 + c) = a[c];
       }
@@ -384,13 +390,7 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
         double a[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) a[c] = TT(r, j0 + c);
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          double v = a[c];
-#pragma unroll
-          for (int k = 0; k < c; k++) v = fma(-a[k], l[c][k], v);
-          a[c] = v * inv[c];
-        }
+        solve8_row(a, l, inv);
 #pragma unroll
         for (int c = 0; c < 8; c++) TT(r, j0 + c) = a[c];
       } else {
@@ -403,11 +403,10 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
             v[k] = (c <= j0 + k) ? x : 0.0;
           }
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            double u = v[k];
+          for (int k = 0; k < 8; k++) {                 // right-looking forward substitution (same rounding, short chain)
+            v[k] *= inv[k];
 #pragma unroll
-            for (int q = 0; q < k; q++) u = fma(-l[k][q], v[q], u);
-            v[k] = u * inv[k];
+            for (int q = k + 1; q < 8; q++) v[q] = fma(-l[q][k], v[k], v[q]);
           }
 #pragma unroll
           for (int k = 0; k < 8; k++) {
