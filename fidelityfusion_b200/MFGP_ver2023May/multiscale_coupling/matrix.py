@@ -1,35 +1,12 @@
 """Matrix_Mapping coupling (reference MFGP_ver2023May/multiscale_coupling/matrix.py:8-90):
-res = high - rho * (low x_1 W_1 ... x_M W_M), mode products on libffgp kernels (trainable W_k, fp32-pinned rho)."""
+res = high - rho * (low x_1 W_1 ... x_M W_M).  The mode products run on the libffgp kernels (tensorly_compat.mode_dot ->
+ffgp_mode_dot_f64) with gradients for the trainable W_k; rho is fp32-pinned and frozen unless `trainable_rho`.
+state_dict keys: `vectors.k`, `rho`."""
 import torch
 
 from ... import tensorly_compat as tl
 from ..utils.dict_tools import update_dict_with_default
-
-
-def _smooth_mapping_matrix(_shape):
-    if _shape[0] < _shape[1]:
-        i = torch.arange(_shape[0], dtype=torch.get_default_dtype()).view(-1, 1)
-        j = torch.arange(_shape[1], dtype=torch.get_default_dtype()).view(1, -1)
-        up_rate = _shape[1] / _shape[0]
-        _init_tensor = torch.ones(_shape[0], _shape[1]) / ((i * up_rate - j) ** 2 + 1)
-        _init_tensor = _init_tensor / _init_tensor.sum(0, keepdim=True)
-        _init_tensor = _init_tensor.transpose(1, 0)
-    elif _shape[0] == _shape[1]:
-        _init_tensor = torch.eye(_shape[0])
-    else:
-        assert False, NotImplemented
-    return _init_tensor
-
-
-def _eye_distribution(_shape):
-    if _shape[0] < _shape[1]:
-        init_tensor = torch.eye(_shape[0])
-        init_tensor = torch.nn.functional.interpolate(init_tensor.reshape(1, 1, *init_tensor.shape), _shape, mode='bilinear')
-        init_tensor = init_tensor.squeeze().T
-    elif _shape[0] == _shape[1]:
-        init_tensor = torch.eye(_shape[0])
-    return init_tensor
-
+from ._coupling import RhoCoupling
 
 default_config = {
     'low_fidelity_shape': None,
@@ -40,39 +17,46 @@ default_config = {
 }
 
 
-class Matrix_Mapping(torch.nn.Module):
+def _smooth_mapping_matrix(shape):
+    """matrix.py:8-24: [h, l] interpolation weights 1 / ((i h/l - j)^2 + 1), columns normalised; identity when l == h."""
+    l, h = shape
+    if l == h:
+        return torch.eye(l)
+    assert l < h, NotImplemented
+    dt = torch.get_default_dtype()
+    src = torch.arange(l, dtype=dt).view(-1, 1) * (h / l)
+    dst = torch.arange(h, dtype=dt).view(1, -1)
+    weight = torch.ones(l, h) / ((src - dst) ** 2 + 1)
+    return (weight / weight.sum(0, keepdim=True)).transpose(1, 0)
+
+
+def _eye_distribution(shape):
+    """matrix.py:26-34: the identity stretched to [l, h] by bilinear interpolation, transposed."""
+    l, h = shape
+    eye = torch.eye(l)
+    if l == h:
+        return eye
+    if l < h:
+        return torch.nn.functional.interpolate(eye.reshape(1, 1, l, l), (l, h), mode='bilinear').squeeze().T
+    return None
+
+
+_INIT = {'smooth': _smooth_mapping_matrix, 'eye': _eye_distribution}
+
+
+class Matrix_Mapping(RhoCoupling):
     def __init__(self, config=None) -> None:
         super().__init__()
         self.config = update_dict_with_default(default_config, config)
-        self.l_shape = self.config['low_fidelity_shape']
-        self.h_shape = self.config['high_fidelity_shape']
+        self.l_shape, self.h_shape = self.config['low_fidelity_shape'], self.config['high_fidelity_shape']
         assert self.l_shape is not None and self.h_shape is not None, \
             "low_fidelity_shape and high_fidelity_shape should be set"
-        vectors = []
-        for i in range(len(self.l_shape)):
-            if self.config['matrix_init_method'] == 'smooth':
-                _init_tensor = _smooth_mapping_matrix((self.l_shape[i], self.h_shape[i]))
-            elif self.config['matrix_init_method'] == 'eye':
-                _init_tensor = _eye_distribution((self.l_shape[i], self.h_shape[i]))
-            vectors.append(torch.nn.Parameter(_init_tensor.contiguous()))
-        self.vectors = torch.nn.ParameterList(vectors)
-        self.rho = torch.nn.Parameter(torch.tensor(self.config['rho_value_init'], dtype=torch.float32))
-        if not self.config['trainable_rho']:
-            self.rho.requires_grad = False
+        init = _INIT[self.config['matrix_init_method']]
+        self.vectors = torch.nn.ParameterList(
+            [torch.nn.Parameter(init((lo, hi)).contiguous()) for lo, hi in zip(self.l_shape, self.h_shape)])
+        self._register_rho(self.config['rho_value_init'], self.config['trainable_rho'])
 
     def _map(self, low_fidelity):
-        for i in range(len(self.l_shape)):
-            low_fidelity = tl.mode_dot(low_fidelity, self.vectors[i], i + 1)
+        for mode, w in enumerate(self.vectors, start=1):
+            low_fidelity = tl.mode_dot(low_fidelity, w, mode)
         return low_fidelity
-
-    def forward(self, low_fidelity, high_fidelity):
-        return high_fidelity - self._map(low_fidelity) * self.rho
-
-    def backward(self, low_fidelity, res):
-        return self._map(low_fidelity) * self.rho + res
-
-    def var_forward(self, low_fidelity_var, high_fidelity_var):
-        return self.forward(low_fidelity_var, high_fidelity_var)
-
-    def var_backward(self, low_fidelity_var, res_var):
-        return self.backward(low_fidelity_var, res_var)
