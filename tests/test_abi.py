@@ -52,3 +52,41 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
     assert rc < 0 and b'null pointer' in lib.ffgp_last_error_string()
     rc = lib.ffgp_syevj_f64(None, 4, 1, None, None, None, 0, None, None)
     assert rc < 0
+
+
+def _header_prototypes():
+    """name -> (return type, [argument C types]) parsed from include/ffgp.h."""
+    src = open(os.path.join(ROOT, 'include', 'ffgp.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r'\b(int|size_t|const char\s*\*|unsigned long long)\s+(ffgp_\w+)\s*\(([^)]*)\)\s*;', src):
+        args = [a.strip() for a in args.split(',')] if args.strip() not in ('', 'void') else []
+        protos[name] = (ret.replace(' ', ''), args)
+    return protos
+
+
+def test_ctypes_signatures_match_the_header(lib):
+    """Every prototype of include/ffgp.h is bound in _lib.py with the same arity and the same pointer / integer / double
+    kind per argument (an ABI drift between the header and the loader would otherwise only show up on the GPU box)."""
+    protos = _header_prototypes()
+    assert len(protos) >= 25
+    for name, (ret, args) in protos.items():
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None or not args, f'{name}: no argtypes declared in _lib.py'
+        at = list(fn.argtypes or [])
+        assert len(at) == len(args), f'{name}: header has {len(args)} arguments, _lib.py binds {len(at)}'
+        for k, (c_arg, ct) in enumerate(zip(args, at)):
+            if '*' in c_arg:
+                want = (ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p)
+            elif re.match(r'(const\s+)?double\b', c_arg):
+                want = (ctypes.c_double,)
+            elif re.match(r'(const\s+)?size_t\b', c_arg):
+                want = (ctypes.c_size_t,)
+            elif re.match(r'(const\s+)?long long\b', c_arg):
+                want = (ctypes.c_longlong,)
+            else:
+                want = (ctypes.c_int,)
+            assert ct in want, f'{name} argument {k} ({c_arg!r}) is bound as {ct}'
+        want_ret = {'int': ctypes.c_int, 'size_t': ctypes.c_size_t, 'constchar*': ctypes.c_char_p,
+                    'unsignedlonglong': ctypes.c_ulonglong}[ret]
+        assert fn.restype is want_ret, f'{name}: return type {fn.restype} != {want_ret}'
