@@ -174,6 +174,50 @@ def test_c3_yvar_many_outputs_tensor_linear():
     assert rel_err(tl2(G(g2['t'])).detach().cpu(), g2['out']) < 1e-12   # only the last mode is applied (sic)
 
 
+def test_c3_full_size_residual_step_vs_oracle():
+    """BASELINE config 3 at full size: the top CIGAR fidelity (CIGAR.py:119-127) - 64x64 field outputs flattened to
+    D = 4096 columns, N = 128 points, d = 5, the 1024 -> 4096 Tensor_linear coupling trained through the residual,
+    N x N y_var - against the CPU oracle on the same inputs: log-likelihood, every gradient (4 M coupling weights
+    included), posterior mean and covariance."""
+    from fidelityfusion_b200.GaussianProcess.gp_computation_pack import Tensor_linear
+    gen = torch.Generator().manual_seed(3)
+    n, d, Dl, Dh, ns = 128, 5, 1024, 4096, 16
+    x = torch.rand(n, d, generator=gen)
+    grid_l, grid_h = torch.linspace(0, 1, Dl), torch.linspace(0, 1, Dh)
+    amp = 1.0 + x[:, :1]
+    y_low = amp * torch.sin(6.0 * grid_l[None, :] + 3.0 * x[:, 1:2]) + 0.3 * torch.cos(9.0 * grid_l[None, :] * x[:, 2:3])
+    y_high = 1.1 * (amp * torch.sin(6.0 * grid_h[None, :] + 3.0 * x[:, 1:2])) + 0.05 * torch.cos(4.0 * grid_h[None, :] + x[:, 3:4])
+    a = torch.rand(n, n, generator=gen)
+    y_var = 0.01 * (a @ a.t()) / n
+    xs = torch.rand(ns, d, generator=gen)
+    ls, sv, lb = np.linspace(0.6, 1.4, d), 1.3, 0.8
+    # oracle (CPU)
+    w0 = O.tensor_linear_init(Dl, Dh).double()
+    wo = w0.clone().requires_grad_(True)
+    lso, svo, lbo = T(ls).requires_grad_(True), torch.tensor([sv], requires_grad=True), torch.tensor([lb], requires_grad=True)
+    res_o = y_high - O.tensor_linear_forward(y_low, [wo])
+    ll_o = O.cigp_log_likelihood(O.ard_kernel(x, x, lso, svo), lbo, res_o, y_var)
+    (-ll_o).backward()
+    with torch.no_grad():
+        mean_o, cov_o = O.cigp_predict(O.ard_kernel(x, x, lso, svo), O.ard_kernel(x, xs, lso, svo),
+                                       O.ard_kernel(xs, xs, lso, svo), lbo, res_o.detach())
+    # CUDA path
+    tl = Tensor_linear([Dl], [Dh]).double().to(DEV)
+    assert rel_err(tl.vectors[0].detach().cpu(), w0) < 1e-12
+    m = _cigp(d, ls, sv, lb)
+    res = G(y_high) - tl(G(y_low))
+    assert rel_err(res.detach().cpu(), res_o.detach()) < TOL
+    ll = m.negative_log_likelihood(G(x), [res, G(y_var)])
+    assert abs(ll.item() - ll_o.item()) <= TOL * abs(ll_o.item())
+    (-ll).backward()
+    assert rel_err(m.kernel.length_scales.grad.cpu(), lso.grad) < TOL
+    assert rel_err(m.kernel.signal_variance.grad.cpu(), svo.grad) < TOL
+    assert rel_err(m.log_beta.grad.cpu(), lbo.grad) < TOL
+    assert rel_err(tl.vectors[0].grad.cpu(), wo.grad) < TOL
+    mean, cov = m(G(x), [res.detach(), G(y_var)], G(xs))
+    assert rel_err(mean.cpu(), mean_o) < TOL and rel_err(cov.cpu(), cov_o) < TOL
+
+
 def test_pack_and_gp_basic():
     from fidelityfusion_b200.GaussianProcess import gp_computation_pack as pack
     from fidelityfusion_b200.GaussianProcess.gp_basic import GP_basic
