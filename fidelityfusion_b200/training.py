@@ -70,13 +70,15 @@ class FusedAdam(torch.optim.Optimizer):
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in active)
         hit = self._tables.get(key)
         if hit is None:
+            for p in active:                           # validate before touching the CUDA runtime: no CPU fallback
+                self._state_for(p)
+                if not (p.grad.is_cuda and p.grad.dtype == torch.float64 and p.grad.is_contiguous()):
+                    raise TypeError('FusedAdam needs contiguous fp64 CUDA gradients')
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError('FusedAdam: the set of (parameter, gradient) buffers changed during CUDA-graph capture; '
                                    'run one eager iteration first (GraphedTrainer does)')
             ptrs = []
             for p in active:
-                if not (p.grad.is_cuda and p.grad.dtype == torch.float64 and p.grad.is_contiguous()):
-                    raise TypeError('FusedAdam needs contiguous fp64 CUDA gradients')
                 st = self._state_for(p)
                 ptrs += [p.data_ptr(), p.grad.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
                          st['step'].data_ptr()]

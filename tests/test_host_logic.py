@@ -108,3 +108,43 @@ def test_factor_cache_token_logic():
     assert c.workspace(128, torch.device('cpu'), ('a', 2))[1] == 0      # grew: buffer reallocated
     c.mark_valid(); c.invalidate()
     assert c.workspace(128, torch.device('cpu'), ('a', 2))[1] == 0
+
+
+def test_next_row_modules_fail_loudly_without_cuda():
+    """SURVEY 8f rows (training loop, data matching, FIDES) follow the same rule as the hot path: no CPU fallback."""
+    from fidelityfusion_b200 import data_match
+    from fidelityfusion_b200.MFGP_ver2023May import FIDES
+    from fidelityfusion_b200.training import FusedAdam, GraphedTrainer
+    p = torch.nn.Parameter(torch.ones(3, dtype=torch.float64))
+    p.grad = torch.ones_like(p)
+    with pytest.raises(TypeError, match='CUDA'):
+        FusedAdam([p], lr=0.1).step()
+    with pytest.raises(_lib.FFGPError):
+        GraphedTrainer(lambda: (p * p).sum(), [p])
+    with pytest.raises(NotImplementedError):
+        FusedAdam([p], amsgrad=True)
+    with pytest.raises(_lib.FFGPError):
+        data_match.row_match(torch.rand(4, 2, dtype=torch.float64), torch.rand(3, 2, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        data_match.row_match(torch.rand(4, 2), torch.rand(3, 5))
+    f = FIDES({}).double()
+    assert list(f.state_dict()) == ['noise_box.value', 'kernel.length_scale', 'kernel.scale', 'kernel.length_scale_z', 'kernel.b']
+    assert f.kernel.noise_exp_format is not True and f.kernel.seed == 1024 and f.forward(torch.rand(2, 2)) is None
+    f.set_fidelity(0., 1., 0., 2.)
+    with pytest.raises(_lib.FFGPError):
+        f.compute_loss(torch.rand(5, 2, dtype=torch.float64), torch.rand(5, 1, dtype=torch.float64))
+
+
+def test_fused_adam_table_cache_is_bounded_and_capture_safe_api():
+    """Host-only behaviour of FusedAdam that does not touch the device: hyper-parameter validation and defaults."""
+    from fidelityfusion_b200.training import FusedAdam
+    p = torch.nn.Parameter(torch.ones(2, dtype=torch.float64))
+    o = FusedAdam([p], lr=0.01)
+    g = o.param_groups[0]
+    assert g['lr'] == 0.01 and g['betas'] == (0.9, 0.999) and g['eps'] == 1e-8 and g['maximize'] is False
+    assert o.losses().numel() == 0
+    o.step()                                     # no gradient anywhere: nothing to do, nothing launched (torch's Adam too)
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdam([p], betas=(1.0, 0.9))
