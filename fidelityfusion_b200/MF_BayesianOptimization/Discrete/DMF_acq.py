@@ -92,11 +92,35 @@ class DiscreteAcquisitionFunction(nn.Module):
         return new_s
 
 
-def optimize_acq_mf(acq, fidelity_num, x_dimension, n_iterations=10, learning_rate=0.001, x_init=None, device='cuda',
-                    dtype=torch.float64):
-    """Candidate optimisation of DMF_acq.py:226-262 (Adam on x, one restart per fidelity, best score wins), with the
-    data manager replaced by explicit sizes.  `acq(x, s)` returns the score of candidate x [1, d] at fidelity s.
-    The reference never zeroes the gradient between steps (optimizer.zero_grad() is commented out, :246-249): kept."""
+def optimize_acq_mf(fidelity_manager, acq_mf, n_iterations=10, learning_rate=0.001):
+    """reference DMF_acq.py:226-262, same signature: Adam on a candidate x per fidelity, the fidelity whose final
+    negative score is smallest wins.  `fidelity_num` and `x_dimension` are read from the data manager as the reference
+    does (:240-241); the candidate is a [d, 1] column (:246, as written) created on the data's device; the gradient is
+    never zeroed between steps (optimizer.zero_grad() is commented out, :247-249) - kept.  `acq_mf(x, s)` is a
+    DiscreteAcquisitionFunction method; the chain d score / d x runs through ffgp_acquisition_f64's partials and the
+    fused posterior gradient."""
+    fidelity_num = int((len(fidelity_manager.data_dict) + 1) / 2)
+    X0 = fidelity_manager.data_dict['0']['X']
+    x_dimension = X0.shape[1]
+    scores, xs = [], []
+    for i in range(fidelity_num):
+        X_initial = nn.Parameter(torch.rand(x_dimension, device=X0.device, dtype=X0.dtype).reshape(-1, 1),
+                                 requires_grad=True)
+        optimizer = torch.optim.Adam([X_initial], lr=learning_rate)
+        for j in range(n_iterations):
+            loss = -1 * acq_mf(X_initial, i)
+            loss.backward()
+            optimizer.step()
+            print('iter', j, 'x:', X_initial, 'Negative Acquisition Function:', loss.item(), end='\n')
+        xs.append(X_initial.detach())
+        scores.append(loss.item())
+    return xs[scores.index(min(scores))]
+
+
+def optimize_acq_candidates(acq, fidelity_num, x_dimension, n_iterations=10, learning_rate=0.001, x_init=None,
+                            device='cuda', dtype=torch.float64):
+    """The same optimisation with explicit sizes and row candidates x [1, d] (no data manager); `x_init[s]` fixes the
+    start point of fidelity s (tests)."""
     best_x, best_loss = None, None
     for s in range(fidelity_num):
         x0 = x_init[s] if x_init is not None else torch.rand(1, x_dimension, device=device, dtype=dtype)

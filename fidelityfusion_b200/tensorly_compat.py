@@ -104,6 +104,40 @@ def ones(shape, **kw):
     return torch.ones(shape, **{k: v for k, v in kw.items() if k in ('device', 'dtype')})
 
 
+_backend = 'pytorch'
+
+
+def set_backend(name, *args, **kwargs):
+    """tensorly.set_backend: six reference files call `tensorly.set_backend('pytorch')` at import
+    (gp_computation_pack.py:12, hogp.py:7, matrix.py:6, both hogp_simple.py:13, GAR_GeneralizedAutoAR.py:11).
+    torch tensors are the only kind handled here, so anything else is an error rather than a silent no-op."""
+    if name != 'pytorch':
+        raise ValueError(f"fidelityfusion_b200.tensorly_compat computes on torch CUDA tensors only (backend 'pytorch'), got {name!r}")
+
+
+def get_backend():
+    return _backend
+
+
+def tensor(data, **kw):
+    return torch.as_tensor(data, **{k: v for k, v in kw.items() if k in ('device', 'dtype')})
+
+
+def to_numpy(t):
+    return t.detach().cpu().numpy()
+
+
+def unfold(t, mode):
+    """tensorly.unfold: mode-`mode` matricisation [I_mode, prod(rest)] (row-major over the remaining modes)."""
+    return torch.movedim(t, mode, 0).reshape(t.shape[mode], -1)
+
+
+def fold(unfolded, mode, shape):
+    shape = list(shape)
+    full = [shape[mode]] + shape[:mode] + shape[mode + 1:]
+    return torch.movedim(unfolded.reshape(full), 0, mode)
+
+
 # ---------------------------------------------------------------------------------------------
 # Kronecker GP core: per-mode eigh -> T1 -> (A, core, sums) -> g, with the analytic gradient
 # ---------------------------------------------------------------------------------------------
@@ -264,3 +298,7 @@ def kron_nll(Y, Ks, tau, add=0.0):
     val, A, g = out[:3]
     eig = [(out[3 + 2 * k], out[4 + 2 * k]) for k in range(len(Ks))]
     return val, A, g, eig
+
+
+# `import tensorly; tensorly.tenalg.mode_dot(...)` (hogp.py:132, matrix.py:73): the alias serves both names
+tenalg = __import__('sys').modules[__name__]

@@ -539,7 +539,7 @@ def test_acquisition_scores_and_partials_match_reference_formulas(kind):
 def test_candidate_optimisation_step_on_device():
     """UCB/EI of the posterior differentiated w.r.t. the candidate through DiscreteAcquisitionFunction ->
     cigp.forward -> ffgp_dense_predict_bwd_f64, against the same composition on the CPU oracle."""
-    from fidelityfusion_b200.MF_BayesianOptimization.Discrete.DMF_acq import DiscreteAcquisitionFunction, optimize_acq_mf
+    from fidelityfusion_b200.MF_BayesianOptimization.Discrete.DMF_acq import DiscreteAcquisitionFunction, optimize_acq_candidates
     gen = torch.Generator().manual_seed(12)
     n, d = 200, 4
     x = torch.rand(n, d, generator=gen)
@@ -565,5 +565,5 @@ def test_candidate_optimisation_step_on_device():
     # the optimiser loop runs and improves the score
     x0 = [xc.clone()]
     s0 = float(acq.UCB_MF(x0[0].to(DEV), 0).item())
-    xb = optimize_acq_mf(lambda xx, s: acq.UCB_MF(xx, s), 1, d, n_iterations=15, learning_rate=0.01, x_init=x0)
+    xb = optimize_acq_candidates(lambda xx, s: acq.UCB_MF(xx, s), 1, d, n_iterations=15, learning_rate=0.01, x_init=x0)
     assert float(acq.UCB_MF(xb, 0).item()) > s0
