@@ -73,13 +73,8 @@ def sep_field(x, shape, modes=4, phase=0.0, scale=1.0):
 # ------------------------------------------------------------------------------------------------------------------
 # gen-2024  (FidelityFusion_Models/)
 # ------------------------------------------------------------------------------------------------------------------
-def case_cigar3_c3(dev, max_iter=20, lr=1e-3, sizes=(512, 256, 128), grids=(16, 32, 64), n_test=64):
-    """BASELINE config 3: CIGAR on a 64x64 field (4096 output columns), 3 fidelities with different output sizes
-    (16^2 / 32^2 / 64^2, flattened), nested inputs, if_nonsubset=True (the only branch of train_CIGAR that runs,
-    SURVEY 8c), unmodified train_CIGAR (CIGAR.py:84-134) + CIGAR.forward (:40-82)."""
-    from FidelityFusion_Models.CIGAR import CIGAR, train_CIGAR
-    from FidelityFusion_Models.MF_data import MultiFidelityDataManager
-    import GaussianProcess.kernel as kernel
+def data_cigar3(dev, sizes=(512, 256, 128), grids=(16, 32, 64), n_test=64):
+    """C3 inputs (SURVEY 8d recipe): nested subsets of U[0,1]^{512x5}, smooth separable fields on 16^2/32^2/64^2 grids."""
     g = torch.Generator(device='cpu').manual_seed(3)
     d = 5
     x_all = torch.rand(sizes[0], d, generator=g, device='cpu')
@@ -89,6 +84,18 @@ def case_cigar3_c3(dev, max_iter=20, lr=1e-3, sizes=(512, 256, 128), grids=(16, 
         xf = x_all[:n]
         yf = (1.0 + 0.1 * f) * sep_field(xf, (s, s)) + 0.05 * f * sep_field(xf, (s, s), modes=2, phase=1.3)
         data.append({'raw_fidelity_name': str(f), 'fidelity_indicator': f, 'X': xf.to(dev), 'Y': yf.reshape(n, -1).to(dev)})
+    return data, xt
+
+
+def case_cigar3_c3(dev, max_iter=20, lr=1e-3, sizes=(512, 256, 128), grids=(16, 32, 64), n_test=64):
+    """BASELINE config 3: CIGAR on a 64x64 field (4096 output columns), 3 fidelities with different output sizes
+    (16^2 / 32^2 / 64^2, flattened), nested inputs, if_nonsubset=True (the only branch of train_CIGAR that runs,
+    SURVEY 8c), unmodified train_CIGAR (CIGAR.py:84-134) + CIGAR.forward (:40-82)."""
+    from FidelityFusion_Models.CIGAR import CIGAR, train_CIGAR
+    from FidelityFusion_Models.MF_data import MultiFidelityDataManager
+    import GaussianProcess.kernel as kernel
+    d = 5
+    data, xt = data_cigar3(dev, sizes, grids, n_test)
     dm = MultiFidelityDataManager(data)
     shapes = [(s * s,) for s in grids]
     model = CIGAR(len(sizes), [kernel.ARDKernel(d) for _ in sizes], shapes, if_nonsubset=True).to(dev)
@@ -170,18 +177,24 @@ def case_nar2_nonsubset(dev):
     return _train_cigp_family(dev, 'NAR', 'train_NAR', 'FidelityFusion_Models.NAR', (90, 45), (None, 30), 20, 1e-2, seed=23)
 
 
-def case_gar2_c4(dev, max_iter=8, lr=1e-2, N=128, shape=(32, 32, 16), n_test=32):
-    """BASELINE config 4 through gen-2024: GAR (GAR.py:13-126) on 32x32x16 tensor outputs, 2 aligned fidelities,
-    HOGP_simple (two_fidelity_models copy) per fidelity, Tensor_linear coupling, unmodified train_GAR."""
-    from FidelityFusion_Models.GAR import GAR, train_GAR
-    from FidelityFusion_Models.MF_data import MultiFidelityDataManager
-    import GaussianProcess.kernel as kernel
+def data_c4(N=128, shape=(32, 32, 16), n_test=32):
+    """C4 inputs (SURVEY 8d recipe): N = 128, d = 5, smooth 32x32x16 fields, Y_hi = 1.1 Y_lo + 0.05 field_2 (CPU tensors)."""
     g = torch.Generator(device='cpu').manual_seed(4)
     d = 5
     x = torch.rand(N, d, generator=g, device='cpu')
     xt = torch.rand(n_test, d, generator=g, device='cpu')
     ylo = sep_field(x, shape)
     yhi = 1.1 * ylo + 0.05 * sep_field(x, shape, modes=3, phase=0.9, scale=2.0)
+    return x, xt, ylo, yhi
+
+
+def case_gar2_c4(dev, max_iter=8, lr=1e-2, N=128, shape=(32, 32, 16), n_test=32):
+    """BASELINE config 4 through gen-2024: GAR (GAR.py:13-126) on 32x32x16 tensor outputs, 2 aligned fidelities,
+    HOGP_simple (two_fidelity_models copy) per fidelity, Tensor_linear coupling, unmodified train_GAR."""
+    from FidelityFusion_Models.GAR import GAR, train_GAR
+    from FidelityFusion_Models.MF_data import MultiFidelityDataManager
+    import GaussianProcess.kernel as kernel
+    x, xt, ylo, yhi = data_c4(N, shape, n_test)
     data = [{'raw_fidelity_name': '0', 'fidelity_indicator': 0, 'X': x.to(dev), 'Y': ylo.to(dev)},
             {'raw_fidelity_name': '1', 'fidelity_indicator': 1, 'X': x.to(dev), 'Y': yhi.to(dev)}]
     dm = MultiFidelityDataManager(data)
@@ -215,19 +228,24 @@ def _adam_loop(model, loss_fn, steps, lr):
     return torch.tensor(losses), g0
 
 
-def case_ar2023_c1(dev, steps=50, lr=0.01):
-    """BASELINE config 1 (SURVEY 8d recipe): gen-2023 AR, 2 fidelities, N = 100, d = 2, D = 64, the epoch loop of
-    mfgp_demo.py:122-127 (Adam lr 0.01, 50 steps on AR.compute_loss, AR_AutoRegression.py:206-254), then AR.forward
-    on the 100 held-out points."""
-    from MFGP_ver2023May import AR
+def data_c1():
+    """C1 inputs (SURVEY 8d recipe, stand-in for the toy data missing from the tree): x ~ U[0,1]^{200x2}, first 100
+    train / last 100 eval, y_lo = sin(2 pi x w), y_hi = 1.2 y_lo + 0.1 cos(3 x_0), z-normalised (CPU tensors)."""
     g = torch.Generator(device='cpu').manual_seed(1)
     xa = torch.rand(200, 2, generator=g, device='cpu')
     w = torch.randn(2, 64, generator=g, device='cpu')
     ylo = torch.sin(2 * math.pi * xa @ w)
     yhi = 1.2 * ylo + 0.1 * torch.cos(3 * xa[:, :1])
     norm = lambda t, ref: (t - ref.mean()) / ref.std()                   # z-normalisation, mfgp_demo.py:25-33 style
-    x, xe = norm(xa[:100], xa[:100]).to(dev), norm(xa[100:], xa[:100]).to(dev)
-    y0, y1 = norm(ylo[:100], ylo[:100]).to(dev), norm(yhi[:100], yhi[:100]).to(dev)
+    return (norm(xa[:100], xa[:100]), norm(xa[100:], xa[:100]), norm(ylo[:100], ylo[:100]), norm(yhi[:100], yhi[:100]))
+
+
+def case_ar2023_c1(dev, steps=50, lr=0.01):
+    """BASELINE config 1 (SURVEY 8d recipe): gen-2023 AR, 2 fidelities, N = 100, d = 2, D = 64, the epoch loop of
+    mfgp_demo.py:122-127 (Adam lr 0.01, 50 steps on AR.compute_loss, AR_AutoRegression.py:206-254), then AR.forward
+    on the 100 held-out points."""
+    from MFGP_ver2023May import AR
+    x, xe, y0, y1 = (t.to(dev) for t in data_c1())
     m = AR({'fidelity_shapes': [(64,), (64,)]}).double().to(dev)
     losses, g0 = _quiet(_adam_loop, m, lambda: m.compute_loss(x, [y0, y1]), steps, lr)
     with torch.no_grad():
@@ -243,12 +261,7 @@ def case_gar2023_c4(dev, steps=5, lr=0.01, N=128, shape=(32, 32, 16), n_test=32)
     GAR.compute_loss (GAR_GeneralizedAutoAR.py:207-250: two HOGPs + Matrix_Mapping residual), all gradients of the
     first step, 5 Adam steps, GAR.forward on 32 points."""
     from MFGP_ver2023May import GAR
-    g = torch.Generator(device='cpu').manual_seed(4)
-    d = 5
-    x = torch.rand(N, d, generator=g, device='cpu')
-    xt = torch.rand(n_test, d, generator=g, device='cpu')
-    ylo = sep_field(x, shape)
-    yhi = 1.1 * ylo + 0.05 * sep_field(x, shape, modes=3, phase=0.9, scale=2.0)
+    x, xt, ylo, yhi = data_c4(N, shape, n_test)
     x, xt, ylo, yhi = x.to(dev), xt.to(dev), ylo.to(dev), yhi.to(dev)
     m = GAR({'fidelity_shapes': [torch.Size(shape)] * 2}).double().to(dev)
     losses, g0 = _quiet(_adam_loop, m, lambda: m.compute_loss(x, [ylo, yhi]), steps, lr)
