@@ -118,7 +118,8 @@ def cpu_eval_c2(torch, threads):
     x, y = c2_inputs(torch)
     ls, sv, lb = torch.ones(D_C2, dtype=torch.float64), torch.ones(1, dtype=torch.float64), torch.ones(1, dtype=torch.float64)
     t0 = time.perf_counter()
-    loss, _ = O.cigp_ard_nll_and_grads(x, y, ls, sv, lb)
+    loss, grads = O.cigp_ard_nll_and_grads(x, y, ls, sv, lb)
+    cpu_eval_c2.last_grads = grads
     return time.perf_counter() - t0, loss
 
 
@@ -341,6 +342,9 @@ def main():
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     nll_val = float(loss.item())
     value = world * 1e3 / ms_step
+    gpu_grads = {'length_scales': model.kernel.length_scales.grad.detach().cpu().clone(),
+                 'signal_variance': model.kernel.signal_variance.grad.detach().cpu().clone(),
+                 'log_beta': model.log_beta.grad.detach().cpu().clone()}
 
     # ------------------------------------------------------------------ e2e: host buffers in, scalars + gradients out
     def one_eval_e2e():
@@ -429,7 +433,10 @@ def main():
         cpu = {'value': 1.0 / dt, 'unit': 'evals/s', 'cores': threads, 'kind': 'port',
                'sample': '1 full NLL+grad eval of the C2 workload (N=8192, d=16) with the oracle port of the reference '
                          f'(torch {torch.__version__} CPU); nll={cpu_loss:.10f}',
-               'gpu_vs_cpu_nll_rel_diff': abs(cpu_loss - nll_val) / abs(cpu_loss)}
+               'gpu_vs_cpu_nll_rel_diff': abs(cpu_loss - nll_val) / abs(cpu_loss),
+               # all 18 hyper-parameter gradients of the same eval, max |gpu - cpu| / max |cpu| per parameter tensor
+               'gpu_vs_cpu_grad_rel_diff': max(
+                   float((gpu_grads[k] - v).abs().max() / v.abs().max()) for k, v in cpu_eval_c2.last_grads.items())}
 
     achieved = F_ALG_C2 * (world * 1e3 / ms_step) * 1e-12 / world      # per-GPU TFLOP/s on algorithmic FLOPs
     line = {

@@ -40,6 +40,10 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     Bn, n, d = x.shape
     D = y.shape[2]
     dev = x.device
+    if not x.is_cuda:
+        raise B.FFGPError('fidelityfusion_b200 operates on CUDA tensors only (no CPU fallback)')
+    if Bn == 0:
+        return empty_result(d, D, 0 if xs is None else xs.shape[1], want_grad, check, dev)
     f64 = lambda t: t.detach().to(torch.float64).contiguous()
     xc, yc = f64(x), f64(y)
     ls, sv, lb = f64(length_scales), f64(signal_variance).reshape(Bn), f64(log_beta).reshape(Bn)
@@ -81,6 +85,20 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     return out
 
 
+def empty_result(d, D, ns, want_grad, check, device):
+    """The result dict of a batch of ZERO problems (a rank whose block is empty when there are fewer problems than
+    ranks): nothing to compute, but the rank still joins the collective with correctly shaped fields."""
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=device)
+    out = {'nll': z(0)}
+    if not check:
+        out['info'] = z(0)
+    if want_grad:
+        out.update(g_length_scales=z(0, d), g_signal_variance=z(0), g_log_beta=z(0))
+    if ns:
+        out.update(mean=z(0, ns, D), var=z(0, ns))
+    return out
+
+
 def check_batch_info(info):
     """Raise what the reference raises for the first problem whose covariance was not positive definite
     (`info` = out['info'] of a check=False evaluation, possibly all-gathered over the ranks).  One host sync."""
@@ -96,7 +114,7 @@ def shard_range(total, rank, world):
 
 def pack_results(res, keys):
     """[B_local, F] buffer: one row per problem, fields in `keys` order, each flattened."""
-    return torch.cat([res[k].reshape(res[k].shape[0], -1) for k in keys], dim=1).contiguous()
+    return torch.cat([res[k].reshape(res[k].shape[0], math.prod(res[k].shape[1:])) for k in keys], dim=1).contiguous()
 
 
 def unpack_results(buf, shapes, keys):
@@ -121,8 +139,11 @@ def sharded_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     Bn = x.shape[0]
     lo, hi = shard_range(Bn, rank, world)
     sl = slice(lo, hi)
-    res = compute_fn(x[sl], y[sl], length_scales[sl], signal_variance[sl], log_beta[sl],
-                     None if xs is None else xs[sl], want_grad, **kw)
+    if hi > lo:
+        res = compute_fn(x[sl], y[sl], length_scales[sl], signal_variance[sl], log_beta[sl],
+                         None if xs is None else xs[sl], want_grad, **kw)
+    else:           # fewer problems than ranks: skip the compute, still join the collective (the others would hang)
+        res = empty_result(x.shape[2], y.shape[2], 0 if xs is None else xs.shape[1], want_grad, check, x.device)
     keys = [k for k in ('nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var', 'info') if k in res]
     shapes = {k: tuple(res[k].shape[1:]) for k in keys}
     local = pack_results(res, keys)

@@ -1,6 +1,7 @@
 // Host side of the dense GP path: workspace layout, the recursive potrf+trtri driver and the
 // C-ABI entry points declared in include/ffgp.h.  No allocation, no host synchronisation.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -17,7 +18,7 @@
 namespace ffgp {
 
 thread_local char g_err[512] = "";
-unsigned long long g_launches = 0;   // kernels launched by this library (bench.py reports it as gpu_launches)
+std::atomic<unsigned long long> g_launches{0};   // kernels launched by this library (bench.py reports it as gpu_launches)
 // FFGP_TRACE=1: a timing event after every level-3 launch of a dense evaluation, dumped (with a host sync) by
 // ffgp_trace_dump() - the timeline tool behind profiles/r01_timeline_*.txt.  Never enabled in production.
 struct TraceRec { const char* what; int a, b; void* stream; cudaEvent_t ev; };
@@ -58,15 +59,16 @@ static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 // ---------------------------------------------------------------------------------------------
 // GEMM dispatch: layout flags -> template instance; tile size by divisibility and machine fill
 // ---------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
 static int num_sms() {
-  if (g_num_sms == 0) {
+  static PerDeviceInt per_dev;
+  int& v = *per_dev.slot();
+  if (v == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
   }
-  return g_num_sms;
+  return v;
 }
 
 // FFGP_GEMM_TMA=0 routes the 128-tile GEMMs through the older cp.async kernel (A/B comparisons only)
@@ -597,8 +599,9 @@ static int debug_stop_after() {
   return v;
 }
 
-static bool g_attr_done = false;
 static cudaError_t ensure_attrs() {
+  static PerDeviceOnce once;
+  bool& g_attr_done = *once.slot();
   if (g_attr_done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
   if (e != cudaSuccess) return e;
@@ -1094,7 +1097,8 @@ int ffgp_row_match_f64(const double* a, const double* b, int na, int nb, int d, 
   if (na <= 0 || nb <= 0 || d <= 0) return fail(-2, "ffgp_row_match_f64: bad size");
   const size_t smem = (size_t)MATCH_ROWS * (2 * d + 1) * sizeof(double);
   if (smem > 200 * 1024) return fail(-2, "ffgp_row_match_f64: d too large (rows of up to 99 values)");
-  static bool attr = false;
+  static PerDeviceOnce once;
+  bool& attr = *once.slot();
   if (!attr) {
     FFGP_CUDA(cudaFuncSetAttribute(row_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;

@@ -22,6 +22,25 @@
 
 namespace ffgp {
 
+// One-shot per-DEVICE initialisation flag.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to
+// the current device's context: a process that drives a second GPU must set them again there.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool* slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return &done[dev & 63];
+  }
+};
+struct PerDeviceInt {
+  int v[64] = {};
+  int* slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return &v[dev & 63];
+  }
+};
+
 enum KMode : int {
   K_FULL = 0,       // k in [0, K)
   K_LE_ROW = 1,     // A lower-triangular in (i,p): k in [0, i0+BM)
@@ -230,7 +249,8 @@ template <int BM, int BN, int BK, int WM_, int WN_, int ST, bool A_KMAJ, bool B_
 cudaError_t launch_cfg(const GemmParams& p, int batch, cudaStream_t st) {
   using Cfg = GemmCfg<BM, BN, BK, WM_, WN_, ST, A_KMAJ, B_KMAJ>;
   auto kern = gemm_dmma_kernel<BM, BN, BK, WM_, WN_, ST, A_KMAJ, B_KMAJ>;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
+  bool& attr_set = *once.slot();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;

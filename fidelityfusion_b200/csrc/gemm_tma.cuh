@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "gemm_dmma.cuh"
 
 namespace ffgp {
@@ -454,7 +455,8 @@ template <bool A_KMAJ, bool B_KMAJ>
 cudaError_t launch_gemm_tma_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TmaGemmParams& tp, int grid,
                                 cudaStream_t st) {
   auto kern = gemm_tma_kernel<A_KMAJ, B_KMAJ>;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
+  bool& attr_set = *once.slot();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -465,16 +467,35 @@ cudaError_t launch_gemm_tma_cfg(const CUtensorMap& mA, const CUtensorMap& mB, co
 }
 
 // Returns cudaErrorNotSupported when the problem cannot go through the TMA kernel (caller uses gemm_dmma_kernel).
-// Work-item counters of the persistent grids ({next, done} per slot), zero at load and rearmed by each launch itself.
+// Work-item counters of the persistent grids: ONE {next, done} pair PER STREAM, zero at load and rearmed by the last CTA
+// of each launch.  Kernels of one stream run one after the other, so a pair is never shared by two launches in flight;
+// launches on different streams (the library's own side streams, several host threads, a graph replay next to eager
+// work) get different pairs.  Under stream capture the persistent mode is switched off: a captured node would freeze
+// the capture stream's pair into the graph, and the graph may later be replayed on any stream.
 constexpr int TG_SCHED_SLOTS = 64;
 __device__ unsigned int g_tg_sched[2 * TG_SCHED_SLOTS];
-inline unsigned int* tg_sched_base() {
-  static unsigned int* base[64] = {nullptr};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  unsigned int*& b = base[dev & 63];
-  if (!b && cudaGetSymbolAddress((void**)&b, g_tg_sched) != cudaSuccess) b = nullptr;
-  return b;
+struct TgSchedTable {
+  std::mutex mu;
+  unsigned int* base[64] = {nullptr};
+  cudaStream_t streams[64][TG_SCHED_SLOTS] = {};
+  int used[64] = {};
+  // counter pair of (current device, stream); nullptr: table full or symbol unavailable (caller launches non-persistent)
+  unsigned int* slot(cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    dev &= 63;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!base[dev] && cudaGetSymbolAddress((void**)&base[dev], g_tg_sched) != cudaSuccess) { base[dev] = nullptr; return nullptr; }
+    for (int i = 0; i < used[dev]; i++)
+      if (streams[dev][i] == st) return base[dev] + 2 * i;
+    if (used[dev] >= TG_SCHED_SLOTS) return nullptr;
+    streams[dev][used[dev]] = st;
+    return base[dev] + 2 * used[dev]++;
+  }
+};
+inline TgSchedTable& tg_sched_table() {
+  static TgSchedTable t;
+  return t;
 }
 
 // `persistent_ctas` > 0: that many CTAs pull work items from a launch-wide counter, so the TMA producer streams the next
@@ -499,11 +520,10 @@ inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p
   int grid = (int)total;
   tp.sched = nullptr;
   if (persistent_ctas > 0 && total > persistent_ctas) {
-    unsigned int* base = tg_sched_base();
-    if (base) {
-      static unsigned int seq = 0;                       // a slot is reused 64 launches later: long after its kernel ended
-      tp.sched = base + 2 * (seq++ % TG_SCHED_SLOTS);
-      grid = persistent_ctas;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+      tp.sched = tg_sched_table().slot(st);
+      if (tp.sched) grid = persistent_ctas;
     }
   }
   if (a_kmaj && b_kmaj) return launch_gemm_tma_cfg<true, true>(mA, mB, tp, grid, st);

@@ -9,6 +9,7 @@
 //   syevj_kernel        cyclic parallel-order Jacobi eigensolver, one CTA per matrix
 //   kernel_bwd_kernel   d(sum gK o K)/d(inv_ls, amp) for a rectangular kernel matrix
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -18,7 +19,7 @@
 
 namespace ffgp {
 int fail(int code, const char* fmt, const char* a);
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 
 #define FFGP_CUDA(x)                                                   \
   do {                                                                 \
@@ -272,7 +273,8 @@ template <bool LAST, int MT>
 static cudaError_t launch_mode_small(const ModeSmallParams& p, int sms, cudaStream_t st) {
   auto kern = mode_dot_small_kernel<LAST, MT>;
   const size_t smem = ((size_t)(MT * 8) * p.SA + (size_t)MS_WARPS * MS_STAGES * MS_STAGE_DOUBLES) * sizeof(double);
-  static bool attr = false;
+  static PerDeviceOnce once;
+  bool& attr = *once.slot();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
@@ -485,7 +487,8 @@ static cudaError_t launch_gram_stream(const double* X, const double* Y, double* 
                                       int Jb, int ns, cudaStream_t st) {
   const size_t smem = std::max((size_t)GS_WARPS * GS_STAGES * GS_STAGE_DOUBLES, (size_t)GS_WARPS * 32 * 34) * sizeof(double);
   auto kern = mode_gram_stream_kernel<INNER1, MT>;
-  static bool attr = false;
+  static PerDeviceOnce once;
+  bool& attr = *once.slot();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
@@ -1046,7 +1049,8 @@ using namespace ffgp;
 extern "C" {
 
 static int ms_num_sms() {
-  static int v = 0;
+  static PerDeviceInt per_dev;
+  int& v = *per_dev.slot();
   if (!v) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1216,7 +1220,8 @@ int ffgp_syevj_f64(const double* A, int n, int batch, double* w, double* V, void
   if (workspace_bytes < ffgp_syevj_workspace_bytes(n, batch)) return fail(-3, "ffgp_syevj_f64: workspace too small%s", "");
   cudaStream_t st = (cudaStream_t)stream;
   const int m = (n + 1) & ~1;
-  static bool attr = false;
+  static PerDeviceOnce once;
+  bool& attr = *once.slot();
   if (!attr) {
     FFGP_CUDA(cudaFuncSetAttribute(syevj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     FFGP_CUDA(cudaFuncSetAttribute(syevj_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1252,7 +1257,8 @@ int ffgp_kernel_matrix_bwd_f64(const double* x1, const double* x2, const double*
   if (n1 <= 0 || n2 <= 0 || d <= 0 || d > 64 || batch <= 0) return fail(-2, "ffgp_kernel_matrix_bwd_f64: bad size (d <= 64)%s", "");
   if (scratch_bytes < ffgp_kernel_matrix_bwd_scratch_bytes(n1, n2, d, batch)) return fail(-3, "ffgp_kernel_matrix_bwd_f64: scratch too small%s", "");
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
+  static PerDeviceOnce once;
+  bool& attr = *once.slot();
   if (!attr) {
     FFGP_CUDA(cudaFuncSetAttribute(kernel_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;

@@ -49,16 +49,32 @@ def check_info(info, what='cholesky'):
 
 
 class _WorkspaceCache:
-    """Reuses the (large) opaque workspace across calls instead of re-allocating it."""
+    """Reuses the (large) opaque workspace across calls instead of re-allocating it.
+
+    One buffer per (device, stream): work enqueued on one stream is ordered, so consecutive calls may share a buffer;
+    calls on different streams (or host threads driving different streams) never do.  A buffer that grows is replaced
+    through the caching allocator, which keeps the old block stream-ordered.  While a CUDA graph is being captured the
+    cache is bypassed: the workspace is allocated inside the capture, i.e. from the graph's private memory pool, so a
+    replay can never write into memory that a later eager call has handed to someone else (a cached buffer
+    captured by pointer was a use-after-free once any larger eager call replaced it)."""
 
     def __init__(self):
-        self.buf = None
+        self.bufs = {}
 
     def get(self, nbytes, device):
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = None
-            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        return self.buf
+        if torch.cuda.is_current_stream_capturing():
+            return torch.empty(nbytes, dtype=torch.uint8, device=device)
+        dev = torch.device(device)
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(dev).cuda_stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self.bufs[key] = buf = None                       # release the old block before asking for the larger one
+            self.bufs[key] = buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return buf
+
+    def clear(self):
+        self.bufs.clear()
 
 
 _ws_cache = _WorkspaceCache()
@@ -344,11 +360,33 @@ class FactorCache:
         self.valid = True
 
 
+class _StateToken:
+    """What a resident factorisation depends on: the parameters (storage address + in-place version) and the training
+    data tensors.  The data tensors are held by STRONG reference and compared by identity: a k-fold loop that passes
+    temporaries `x[idx]`, `y[idx]` per call gets the same address back from the caching allocator with version 0 and
+    the same shape - (data_ptr, _version, shape) alone called that a cache hit and predicted from the previous fold's
+    factor.  While the cache holds the token the old tensors stay alive, so their address cannot be handed
+    out again, and a new tensor object is never `is` the old one."""
+    __slots__ = ('params', 'tensors', 'versions')
+
+    def __init__(self, module, tensors):
+        self.params = tuple((p.data_ptr(), p._version) for p in module.parameters())
+        self.tensors = tuple(t for t in tensors if isinstance(t, torch.Tensor))
+        self.versions = tuple(t._version for t in self.tensors)
+
+    def __eq__(self, other):
+        return (isinstance(other, _StateToken) and self.params == other.params and self.versions == other.versions and
+                len(self.tensors) == len(other.tensors) and all(a is b for a, b in zip(self.tensors, other.tensors)))
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+
 def state_token(module, *tensors):
     """Identity + in-place version of every parameter and data tensor a factorisation depends on."""
-    items = [(p.data_ptr(), p._version) for p in module.parameters()]
-    items += [(t.data_ptr(), t._version, tuple(t.shape)) for t in tensors if isinstance(t, torch.Tensor)]
-    return tuple(items)
+    return _StateToken(module, tensors)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -52,7 +52,7 @@ def _worker(rank, world, port, Bn, q, check=True):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('Bn', [6, 7])
+@pytest.mark.parametrize('Bn', [6, 7, 1])          # 1: rank 1's block is empty and must still join the all-gather
 def test_sharded_eval_two_ranks_gloo(Bn):
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context('spawn')

@@ -432,6 +432,30 @@ def test_c2_full_size_anchor_and_gradient_identity():
         assert abs(fd - g0) <= 1e-6 * max(abs(g0), 1.0), (name, fd, g0)
 
 
+def test_c2_full_size_every_gradient_vs_oracle():
+    """BASELINE config 2 at full size (N=8192, d=16): NLL, all 16 length-scale gradients, signal-variance and log_beta
+    gradients and dNLL/dY against ONE evaluation of the CPU oracle (the reference's torch route: cdist kernel ->
+    linalg.cholesky -> triangular solve -> autograd), at a perturbed parameter point (length_scales spread over
+    [0.8, 1.7] with one negative entry for the abs() branch, signal_variance 1.3, log_beta 0.5); 1e-9 relative."""
+    n, d = 8192, 16
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(n, d, generator=gen)
+    y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn(n, 1, generator=gen)
+    ls = 0.8 + 0.06 * torch.arange(d, dtype=torch.float64)
+    ls[3] = -ls[3]
+    sv, lb = 1.3, 0.5
+    m = _cigp(d, ls.numpy(), sv, lb)
+    yy = y.to(DEV).requires_grad_(True)
+    ll = m.negative_log_likelihood(x.to(DEV), yy)
+    (-ll).backward()
+    loss, gr = O.cigp_ard_nll_and_grads(x, y, ls, T([sv]), T([lb]), want_y_grad=True)
+    assert abs(-ll.item() - loss) <= TOL * abs(loss)
+    assert rel_err(m.kernel.length_scales.grad.cpu(), gr['length_scales']) < TOL
+    assert rel_err(m.kernel.signal_variance.grad.cpu(), gr['signal_variance']) < TOL
+    assert rel_err(m.log_beta.grad.cpu(), gr['log_beta']) < TOL
+    assert rel_err(yy.grad.cpu(), gr['y']) < TOL
+
+
 def test_kernel_matrix_input_gradients_match_reference_golden():
     from fidelityfusion_b200.GaussianProcess.kernel import ARDKernel
     g = load_golden('predict_dx')

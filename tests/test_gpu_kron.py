@@ -134,6 +134,74 @@ def test_hogp2023_nondefault_params_and_y_gradient():
     assert rel_err(u.cpu(), g['u']) < 1e-8 and rel_err(v.cpu(), g['var']) < 1e-8
 
 
+def _richardson(f, p0, h):
+    """Central differences at h, h/2, h/4 with two Richardson eliminations (error O(h^6) + eps |f| / h)."""
+    D = [(f(p0 + hh) - f(p0 - hh)) / (2 * hh) for hh in (h, h / 2, h / 4)]
+    r1, r2 = (4 * D[1] - D[0]) / 3, (4 * D[2] - D[1]) / 3
+    return (16 * r2 - r1) / 15
+
+
+def hogp_hyper_gradient_arbiter(g):
+    """d loss / d (length_scale_k, scale_k, noise) of the `hogp2023_params` case by extrapolated central differences of
+    the CPU oracle's loss (no differentiation through eigh at all).  Returns {golden key: value}."""
+    x, Y = T(g['x']), T(g['Y'])
+    shape = Y.shape[1:]
+    ins = [x] + [torch.arange(s, dtype=torch.float64).reshape(-1, 1) for s in shape]
+    ls0 = [0.2 * (i + 1) - 0.3 for i in range(4)]
+    sc0 = [0.1 * (i + 1) for i in range(4)]
+
+    def loss(ls, sc, noise):
+        Ks = [O.se_kernel(ins[k], ins[k], T(ls[k]), T(sc[k]), False) for k in range(4)]
+        return float(O.hogp_loss(Ks, 1.0 / T(noise), Y)[0])
+
+    out = {}
+    for k in range(4):
+        def f_ls(v, k=k):
+            return loss(ls0[:k] + [v] + ls0[k + 1:], sc0, 3.0)
+
+        def f_sc(v, k=k):
+            return loss(ls0, sc0[:k] + [v] + sc0[k + 1:], 3.0)
+        out[f'g_kernel_list_{k}_length_scale'] = _richardson(f_ls, ls0[k], 0.01 * abs(ls0[k]))
+        out[f'g_kernel_list_{k}_scale'] = _richardson(f_sc, sc0[k], 0.02 * abs(sc0[k]))
+    out['g_noise_box_value'] = _richardson(lambda v: loss(ls0, sc0, v), 3.0, 0.03)
+    return out
+
+
+def test_hogp_hyper_gradient_arbiter():
+    """Which side of the 1e-6 disagreement on HOGP kernel-parameter gradients carries the error?  The reference
+    differentiates THROUGH torch.linalg.eigh (hogp.py:18-22; backward has 1/(lambda_i - lambda_j) terms, ill-conditioned
+    for the near-degenerate spectra of smooth kernel matrices); we use the closed form dL/dK_k = U_k (...) U_k^T.
+    Arbiter: Richardson-extrapolated central differences of the loss itself.  Ours must match the arbiter at the
+    north-star 1e-9 on every parameter; the reference's own autograd values are compared too and reported."""
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    g = load_golden('hogp2023_params')
+    arb = hogp_hyper_gradient_arbiter(g)
+    h = HOGP({'fidelity_shapes': [torch.Size([8, 8, 4])]}).double()
+    with torch.no_grad():
+        h.noise_box.value.fill_(3.0)
+        for i, k in enumerate(h.kernel_list):
+            k.length_scale.fill_(0.2 * (i + 1) - 0.3)
+            k.scale.fill_(0.1 * (i + 1))
+    h = h.to(DEV)
+    h.compute_loss(G(g['x']), G(g['Y'])).backward()
+    ours = {'g_noise_box_value': float(h.noise_box.value.grad)}
+    for k in range(4):
+        ours[f'g_kernel_list_{k}_length_scale'] = float(h.kernel_list[k].length_scale.grad)
+        ours[f'g_kernel_list_{k}_scale'] = float(h.kernel_list[k].scale.grad)
+    scale = max(abs(v) for v in arb.values())
+    rows = []
+    for key, a in arb.items():
+        ref = float(g[key])
+        e_ours = abs(ours[key] - a) / max(abs(a), 1e-3 * scale)
+        e_ref = abs(ref - a) / max(abs(a), 1e-3 * scale) if np.isfinite(ref) else float('inf')
+        rows.append((key, a, e_ours, e_ref))
+    print('\nHOGP hyper-gradient arbiter (rel. error vs extrapolated central differences): key, value, ours, reference autograd')
+    for key, a, eo, er in rows:
+        print(f'  {key:34s} {a:+.12e}  ours {eo:.1e}  reference {er:.1e}')
+    bad = [(key, eo) for key, a, eo, er in rows if not eo < 1e-9]
+    assert not bad, bad
+
+
 def test_c4_GAR2023_two_fidelity_loss_grads_predict():
     """C4: gen-2023 GAR = HOGP on fidelity 0 + HOGP on the Matrix_Mapping residual (GAR_GeneralizedAutoAR.py:207-250)."""
     from fidelityfusion_b200.MFGP_ver2023May import HOGP
