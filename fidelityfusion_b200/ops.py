@@ -62,6 +62,8 @@ class _WorkspaceCache:
         self.bufs = {}
 
     def get(self, nbytes, device):
+        if torch.device(device).type != 'cuda':
+            raise B.FFGPError('fidelityfusion_b200 operates on CUDA tensors only (no CPU fallback)')
         if torch.cuda.is_current_stream_capturing():
             return torch.empty(nbytes, dtype=torch.uint8, device=device)
         dev = torch.device(device)
