@@ -41,6 +41,7 @@ def lib():
     _sig(L.ffgp_last_error_string, ctypes.c_char_p, [])
     _sig(L.ffgp_launch_count, ctypes.c_ulonglong, [])
     _sig(L.ffgp_trace_dump, i, [])
+    _sig(L.ffgp_debug_last_eigh_sweeps, i, [])
     _sig(L.ffgp_gemm_f64, i, [i, i, vp, i, ll, vp, i, ll, vp, i, ll, i, i, i, ctypes.c_double, ctypes.c_double, i, i, i, vp])
     _sig(L.ffgp_kernel_matrix_f64, i, [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp])
     _sig(L.ffgp_kernel_matrix_bwd_scratch_bytes, sz, [i, i, i, i])

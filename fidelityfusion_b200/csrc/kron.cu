@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include "../../include/ffgp.h"
 #include "gemm_dmma.cuh"
+#include "syevj_hestenes.cuh"
 
 namespace ffgp {
 int fail(int code, const char* fmt, const char* a);
@@ -1229,6 +1230,17 @@ int ffgp_syevj_f64(const double* A, int n, int batch, double* w, double* V, void
   }
   double* vt = (double*)workspace;
   FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+  // n <= 128: one-sided Jacobi with register-resident column pairs (syevj_hestenes.cuh).  FFGP_EIGH=twosided keeps the
+  // round-1 two-sided cluster kernel (A/B comparisons only).
+  static int hestenes = -1;
+  if (hestenes < 0) { const char* e = getenv("FFGP_EIGH"); hestenes = (e && strcmp(e, "twosided") == 0) ? 0 : 1; }
+  if (n <= HJ_MAX_N && hestenes) {
+    static int sweeps = -1;              // FFGP_EIGH_SWEEPS=k: cap the sweeps (timing one sweep; results then unconverged)
+    if (sweeps < 0) { const char* e = getenv("FFGP_EIGH_SWEEPS"); sweeps = e ? atoi(e) : 30; }
+    FFGP_CUDA(hj_launch(A, n, batch, w, V, info, sweeps, st));
+    ++ffgp::g_launches;
+    return 0;
+  }
   if (n <= SYEVJ_SMEM_N) {
     const int half = m / 2;
     const size_t smem = ((size_t)m * (m + 1) + 4 * half) * sizeof(double) + (size_t)(4 * half + m + 2) * sizeof(int) +
@@ -1242,6 +1254,14 @@ int ffgp_syevj_f64(const double* A, int n, int batch, double* w, double* V, void
   ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Debug only (host sync): Jacobi sweeps of the most recent ffgp_syevj_f64 solve with n <= 128 (problem 0 of the batch).
+int ffgp_debug_last_eigh_sweeps(void) {
+  int v = -1;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(&v, g_hj_last_sweeps, sizeof(int)) != cudaSuccess) return -1;
+  return v;
 }
 
 size_t ffgp_kernel_matrix_bwd_scratch_bytes(int n1, int n2, int d, int batch) {

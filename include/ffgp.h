@@ -29,6 +29,7 @@ extern "C" {
 int ffgp_version(void);
 const char* ffgp_last_error_string(void);  /* host string, thread-local */
 int ffgp_trace_dump(void);                  /* debug: with FFGP_TRACE=1, print the recorded launch timeline (host sync) */
+int ffgp_debug_last_eigh_sweeps(void);      /* debug: Jacobi sweeps of the most recent ffgp_syevj_f64 solve with n <= 128 (host sync) */
 unsigned long long ffgp_launch_count(void); /* kernels launched by the library so far (host counter) */
 
 /* ---------------------------------------------------------------------------------------

@@ -105,6 +105,8 @@ if not a.only or 'eigh' in a.only:
         K = torch.exp(-0.5 * torch.cdist(x, x) ** 2)
         sec = timeit(lambda: tl.eigh(K), flush=False)
         report(f'syevj n={n} (incl. python wrapper + info readback)', sec)
+        sec = timeit(lambda: tl._eigh_launch(K), flush=False)
+        report(f'syevj n={n} (kernel enqueue only, no status readback)', sec)
         sec = timeit(lambda: torch.linalg.eigh(K), flush=False)
         report(f'[torch.linalg.eigh / cuSOLVER] n={n}', sec)
 
