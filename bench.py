@@ -212,6 +212,11 @@ def kron_numbers(torch):
     out['hogp_c4_loss_grad_ms'] = med(step) * 1e3
     K = torch.exp(-0.5 * torch.cdist(x, x) ** 2)
     out['eigh_n128_ms'] = med(lambda: tl.eigh(K)) * 1e3
+    out['eigh_n128_cusolver_ms'] = med(lambda: torch.linalg.eigh(K)) * 1e3        # the library kernel it replaces, same box
+    for n_small in (32, 16):
+        Ks = K[:n_small, :n_small].contiguous()
+        out[f'eigh_n{n_small}_ms'] = med(lambda: tl.eigh(Ks)) * 1e3
+        out[f'eigh_n{n_small}_cusolver_ms'] = med(lambda: torch.linalg.eigh(Ks)) * 1e3
     return out
 
 
@@ -245,6 +250,69 @@ def training_numbers(torch, iters=100):
             'graph_replay_fused_adam_ms_per_epoch': graphed, 'final_loss': float(tr.losses()[-1])}
 
 
+def reference_cuda_numbers(torch):
+    """INFORMATIONAL ("these library calls are the existing kernels the new sm_100a kernels must beat on the
+    same box"): what the reference itself does when a user moves its tensors to the GPU - the oracle port executed on
+    CUDA tensors, i.e. torch.cdist / cuBLAS, cuSOLVER potrf + trsm, syevd and autograd through them.  No parity or
+    roofline claim rides on these numbers; they are the library baseline beside ours, same box, same run."""
+    from oracle import ff_oracle as O
+    out = {'what': 'oracle port (the reference torch call sequence) on CUDA tensors: cuBLAS / cuSOLVER / autograd'}
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # C2: one NLL + gradient evaluation, N = 8192, d = 16
+    x, y = [t.cuda() for t in c2_inputs(torch)]
+    ls, sv, lb = (torch.ones(D_C2, device='cuda'), torch.ones(1, device='cuda'), torch.ones(1, device='cuda'))
+    ms = timed(lambda: O.cigp_ard_nll_and_grads(x, y, ls, sv, lb), 3)
+    out['c2_ms_per_eval'] = ms
+    out['c2_evals_per_s'] = 1e3 / ms
+    del x, y
+    torch.cuda.empty_cache()
+    # C5: 64 of the 4096 problems, sequentially like the reference's Python loops (v1/CFKG.py:124-129)
+    bx, by, bls, bsv, blb, bxs = [t.cuda() for t in c5_inputs(torch, 0, 64)]
+
+    def c5_loop():
+        for b in range(64):
+            O.cigp_ard_nll_and_grads(bx[b], by[b], bls[b], bsv[b:b + 1], blb[b:b + 1])
+            O.cigp_ard_predict(bx[b], by[b], bxs[b], bls[b], bsv[b:b + 1], blb[b:b + 1])
+    ms = timed(c5_loop, 2)
+    out['c5_gps_per_s_sequential_loop'] = 64 / ms * 1e3
+    # the same 64 problems batched through torch's own batched kernels (what a user could write with torch alone)
+    def c5_batched():
+        l = bls.clone().requires_grad_(True); s_ = bsv.clone().requires_grad_(True); b_ = blb.clone().requires_grad_(True)
+        ell = l.abs() + 1e-9
+        K = s_.abs().view(-1, 1, 1) * torch.exp(-0.5 * torch.cdist(bx / ell.unsqueeze(1), bx / ell.unsqueeze(1)) ** 2)
+        Sig = K + (torch.exp(-b_) + 1e-6).view(-1, 1, 1) * torch.eye(N_C5, device='cuda')
+        Lc = torch.linalg.cholesky(Sig)
+        gam = torch.linalg.solve_triangular(Lc, by, upper=False)
+        nll = 0.5 * (gam ** 2).sum((1, 2)) + torch.log(torch.diagonal(Lc, dim1=1, dim2=2)).sum(1)
+        nll.sum().backward()
+    ms = timed(c5_batched, 3)
+    out['c5_gps_per_s_torch_batched_nll_grad_only'] = 64 / ms * 1e3
+    del bx, by
+    # C4: one HOGP loss + gradient, 128 x 32 x 32 x 16 (eigh through cuSOLVER syevd, autograd through it)
+    g = torch.Generator().manual_seed(4)
+    xk = torch.rand(128, 5, generator=g, dtype=torch.float64).cuda()
+    Y = torch.randn(128, 32, 32, 16, generator=g, dtype=torch.float64).cuda()
+    grids = [xk] + [torch.arange(s_, dtype=torch.float64, device='cuda').reshape(-1, 1) for s_ in (32, 32, 16)]
+
+    def hogp():
+        p = [torch.ones(2, device='cuda', requires_grad=True) for _ in range(4)]
+        nz = torch.ones(1, device='cuda', requires_grad=True)
+        Ks = [O.se_kernel(grids[k], grids[k], p[k][0], p[k][1], False) for k in range(4)]
+        loss, _, _ = O.hogp_loss(Ks, 1.0 / nz, Y)
+        loss.backward()
+    out['c4_hogp_loss_grad_ms'] = timed(hogp, 5)
+    return out
+
+
 def measure_dgemm_peak(torch):
     """FP64 roofline denominator: cuBLAS DGEMM 8192^3 through torch.matmul, best of 10 (MEASURED_PEAKS.json
     has no fp64 entry)."""
@@ -272,7 +340,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--skip-batched', action='store_true')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
-    ap.add_argument('--skip-kron', action='store_true')
+    ap.add_argument('--skip-kron', action='store_true', help='skip the secondary kron / training / reference_cuda blocks')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 0)
     if args.impl == 'reference':
@@ -469,6 +537,11 @@ def main():
             line['training'] = training_numbers(torch)
         except Exception as e:
             line['training'] = {'error': repr(e)[:300]}
+        try:
+            torch.cuda.empty_cache()
+            line['reference_cuda'] = reference_cuda_numbers(torch)
+        except Exception as e:
+            line['reference_cuda'] = {'error': repr(e)[:300]}
     if batched is not None:
         batched['roofline_frac'] = batched['tflops_alg'] / world / peak_tflops if peak_tflops else None
         line['batched'] = batched

@@ -20,6 +20,11 @@ class cigp(nn.Module):
         self.kernel = kernel
         self.log_beta = nn.Parameter(torch.tensor([log_beta]))
         self.factor_cache = ops.FactorCache()   # L^-1 and alpha stay on the device between forward() calls
+        # forward() treats hyper-parameters and training data as constants of the posterior (fast path: resident factor,
+        # gradient w.r.t. x_test only - what the acquisition optimisers use).  The reference's posterior is an ordinary
+        # autograd expression in EVERYTHING (cigp_v10.py:24-48); set this to True to get that: the kernel matrices are
+        # materialised and the conditional runs through the differentiable covariance-input path.
+        self.differentiable_posterior = False
 
     @staticmethod
     def _split(y_train):
@@ -32,6 +37,13 @@ class cigp(nn.Module):
         entry and y_var is ignored, exactly as cigp_v10.py:24-48."""
         y_train, _ = self._split(y_train)
         noise = self.log_beta.exp().pow(-1)
+        if self.differentiable_posterior and torch.is_grad_enabled():
+            from .gp_computation_pack import conditional_Gaussian
+            n = x_train.size(0)
+            eye = torch.eye(n, dtype=y_train.dtype, device=y_train.device)
+            Sigma = self.kernel(x_train, x_train) + noise * eye + JITTER * eye
+            mean, cov = conditional_Gaussian(y_train, Sigma, self.kernel(x_train, x_test), self.kernel(x_test, x_test))
+            return mean, cov + noise
         fp = fused_or_none(self.kernel)
         diag = (noise + JITTER).reshape(1)
         if fp is not None:

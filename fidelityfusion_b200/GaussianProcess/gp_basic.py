@@ -2,7 +2,9 @@
 import torch
 import torch.nn as nn
 
-from .gp_computation_pack import Gaussian_log_likelihood, conditional_Gaussian
+import numpy as np
+
+from .gp_computation_pack import Gaussian_log_likelihood, conditional_Gaussian, _SolveLogdet, _mm
 
 
 class GP_basic(nn.Module):
@@ -30,4 +32,9 @@ class GP_basic(nn.Module):
 
     def log_likelihood(self, x_train, y_train, Kinv_method='cholesky3'):
         K, y_train = self._cov(x_train, y_train)
+        if Kinv_method == 'cholesky2':
+            # gp_basic.py:122-125 sums the D x D matrix gamma^T gamma (the pack function returns the matrix, :62-65)
+            n = len(x_train)
+            alpha, logdet = _SolveLogdet.apply(y_train, K)
+            return -0.5 * (_mm(alpha.T.contiguous(), alpha).sum() + 2 * logdet + n * np.log(2 * np.pi))
         return Gaussian_log_likelihood(y_train, K, Kinv_method)

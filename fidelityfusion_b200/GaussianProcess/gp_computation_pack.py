@@ -16,11 +16,14 @@ JITTER = 1e-6
 PI = 3.1415
 
 
-class _CholPieces(torch.autograd.Function):
-    """One CUDA factorisation of a given covariance -> (qL, qS, logdet):
-       qL = ||L^-1 y||_F^2 = tr(y^T S y),  qS = ||S y||_F^2  (S = Sigma^-1),  logdet = log|Sigma|.
-    The reference's 'cholesky2/3' variants put cholesky_solve(y, L) = S y inside the square
-    (gp_computation_pack.py:62-80), 'cholesky1/direct' use y^T S y; both are provided."""
+def _mm(A, B):
+    """A @ B for 2-D operands on libffgp's DMMA mode-product kernels (autograd-aware): (A @ B) = B x_0 A."""
+    return mode_dot(B, A, 0)
+
+
+class _SolveLogdet(torch.autograd.Function):
+    """One CUDA factorisation of a given covariance -> (alpha = Sigma^-1 Y, log|Sigma|), differentiable in Y and Sigma.
+    Every `Kinv_method` variant of the reference is an expression in these two (gp_computation_pack.py:55-88)."""
 
     @staticmethod
     def forward(ctx, y, cov):
@@ -44,46 +47,63 @@ class _CholPieces(torch.autograd.Function):
         B.check(rc, 'ffgp_dense_nll_f64')
         ops.check_info(info)
         a = alpha[0]
-        qL = 2.0 * core[0] - D * logdet[0]
         if want:
-            S = (2.0 * G[0] + a @ a.T) / D          # G = 0.5 (D S - a a^T)
+            # the kernel returns G = 0.5 (D S - a a^T), S = Sigma^-1 (symmetric): recover S with our own product
+            S = (2.0 * G[0] + _mm(a, a.T.contiguous())) / D
             ctx.save_for_backward(a, S)
-        return qL.to(y.dtype), (a ** 2).sum().to(y.dtype), logdet[0].to(y.dtype)
+        ctx.dt = (y.dtype, cov.dtype)
+        return a.to(y.dtype), logdet[0].to(y.dtype)
 
     @staticmethod
-    def backward(ctx, gqL, gqS, gld):
+    def backward(ctx, g_alpha, g_logdet):
         a, S = ctx.saved_tensors
-        b = S @ a
-        gy = 2.0 * a * gqL + 2.0 * b * gqS
-        gS = -(a @ a.T) * gqL - (b @ a.T + a @ b.T) * gqS + S * gld
+        ydt, cdt = ctx.dt
+        b = _mm(S, ops._f64c(g_alpha))                    # Sigma^-1 g_alpha
+        gy = b.to(ydt) if ctx.needs_input_grad[0] else None
+        gS = None
+        if ctx.needs_input_grad[1]:
+            gS = (-_mm(b, a.T.contiguous()) + g_logdet.to(torch.float64) * S).to(cdt)
         return gy, gS
 
 
 def Gaussian_log_likelihood(y, cov, Kinv_method='cholesky3'):
-    """reference gp_computation_pack.py:34-91.  All Cholesky variants run the same CUDA factorisation;
-    what differs is the expression the reference forms from it (reproduced as written)."""
+    """reference gp_computation_pack.py:34-91.  All variants run the same CUDA factorisation; what differs is the
+    expression the reference forms from it, reproduced as written: 'cholesky1' / 'direct' use y^T Sigma^-1 y (a D x D
+    matrix for D columns), 'cholesky2' / 'cholesky3' put cholesky_solve(y, L) = Sigma^-1 y inside the square
+    (SURVEY A-12), the torch_distribution variants evaluate a MultivariateNormal centred on y at y."""
     assert len(y.shape) == 2 and len(cov.shape) == 2, "y, mean, cov should be 2D tensors"
     n, D = y.shape
-    qL, qS, logdet = _CholPieces.apply(y, cov)
+    if Kinv_method in ('torch_distribution_MN1', 'torch_distribution_MN2'):
+        # MultivariateNormal(loc=y, ...).log_prob(y): the event size is y.shape[1] and must equal len(cov) (:85-88);
+        # the deviation is zero, so every batch row gets -0.5 (n log 2 pi + log|cov|)
+        if D != cov.shape[0]:
+            raise ValueError(f'MultivariateNormal: loc has event size {D} but the covariance is {cov.shape[0]} x {cov.shape[1]}')
+        _, logdet = _SolveLogdet.apply(y[:, :1], cov)
+        return (-0.5 * (D * np.log(2 * np.pi) + logdet)).expand(n)
+    alpha, logdet = _SolveLogdet.apply(y, cov)
     if Kinv_method in ('cholesky1', 'direct'):
-        if D != 1:
-            raise NotImplementedError("Kinv_method 'cholesky1'/'direct' is provided for single-column y")
-        return -0.5 * (qL + 2 * logdet + n * np.log(2 * np.pi)).reshape(1, 1)
+        return -0.5 * (_mm(y.T.contiguous(), alpha) + 2 * logdet + n * np.log(2 * np.pi))
     if Kinv_method == 'cholesky2':
-        if D != 1:
-            raise NotImplementedError("Kinv_method 'cholesky2' is provided for single-column y")
-        return -0.5 * (qS + 2 * logdet + n * np.log(2 * np.pi)).reshape(1, 1)
+        return -0.5 * (_mm(alpha.T.contiguous(), alpha) + 2 * logdet + n * np.log(2 * np.pi))
     if Kinv_method == 'cholesky3':
         if D > 1:
-            return -0.5 * (qS + logdet * D + n * D * np.log(2 * np.pi))
-        return -0.5 * (qS + logdet + n * np.log(2 * np.pi)).reshape(1, 1)
+            return -0.5 * ((alpha ** 2).sum() + logdet * D + n * D * np.log(2 * np.pi))
+        return -0.5 * ((alpha ** 2).sum() + logdet + n * np.log(2 * np.pi)).reshape(1, 1)
     raise ValueError('Kinv_method should be either direct or cholesky')
 
 
 def conditional_Gaussian(y, Sigma, K_s, K_ss, Kinv_method='cholesky3'):
-    """reference gp_computation_pack.py:93-118: mu = K_s^T Sigma^-1 y, cov = K_ss - (L^-1 K_s)^T (L^-1 K_s)."""
+    """reference gp_computation_pack.py:93-118: mu = K_s^T Sigma^-1 y, cov = K_ss - (L^-1 K_s)^T (L^-1 K_s).
+    Without gradient tracking: one fused prediction call.  With it (any input requires grad under grad mode - the
+    reference's posterior is an ordinary autograd expression): ONE factorisation with the right-hand sides [y, K_s],
+    mu and cov formed from Sigma^-1 [y, K_s] with our own products, differentiable in all four inputs."""
     if Kinv_method not in ('cholesky1', 'cholesky3', 'direct'):
         raise ValueError('Kinv_method should be either direct or cholesky')
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (y, Sigma, K_s, K_ss)):
+        D = y.shape[1]
+        sol, _ = _SolveLogdet.apply(torch.cat([y, K_s], 1), Sigma)
+        KsT = K_s.T.contiguous()
+        return _mm(KsT, sol[:, :D].contiguous()), K_ss - _mm(KsT, sol[:, D:].contiguous())
     with torch.no_grad():
         mu, cov = ops.dense_predict(None, y, None, None, None, sigma_add=Sigma, Ks=K_s, Kss=K_ss, full_cov=True)
     return mu, cov

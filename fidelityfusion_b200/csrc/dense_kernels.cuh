@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixPa
 constexpr int BASE_N = 128;                                  // block size of the single-problem path (and of the padding)
 constexpr int BASE_N_BATCHED = 64;                           // experimental batched base block (see factor_rec); also the log-det slot size
 constexpr int BASE_F = 48;                                   // 36 factor entries + 8 inverses + fail column (+pad)
-constexpr size_t base_smem_bytes(int bn) { return ((size_t)bn * (bn + 1) + 2 * BASE_F + 64 + 64 + 8) * sizeof(double); }
+constexpr size_t base_smem_bytes(int bn) { return ((size_t)bn * (bn + 1) + 2 * BASE_F + 64 + 64 + 8 + 256) * sizeof(double); }
 constexpr size_t BASE_SMEM = base_smem_bytes(BASE_N);
 
 #ifdef FFGP_BASE_TRACE
@@ -253,8 +253,10 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
   double* F = sm + BASE_N * BASE_LD;                // [2][BASE_F] published diagonal factors (double-buffered)
   double* Dn = F + 2 * BASE_F;                      // [36] updated next diagonal block (warp 0 scratch)
   double* red = Dn + 64;
-  const int DUMMY = BASE_N * BASE_LD + 2 * BASE_F + 128;   // sink for masked stores
+  // sink for masked stores / source of masked loads: one slot PER THREAD, so that the branch-free masking below is not a
+  // (benign) shared-memory race between threads - compute-sanitizer racecheck stays clean (profiles/r02_sanitizer.txt)
   const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int DUMMY = BASE_N * BASE_LD + 2 * BASE_F + 136 + tid;
   A += b * sbatch; L += b * sbatch; M += b * sbatch;
 #define TT(i, k) T[(i) * BASE_LD + (k)]
   // block load: every element is an independent 8-byte cp.async (all in flight at once; a plain load loop
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
           double v[8];
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            const double x = TT(c, j0 + k + 1);
+            const double x = T[(c <= j0 + k) ? c * BASE_LD + j0 + k + 1 : DUMMY];
             v[k] = (c <= j0 + k) ? x : 0.0;
           }
 #pragma unroll
@@ -445,10 +447,11 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
 #pragma unroll
         for (int a = 0; a < 4; a++) {
           const int i = i0 + a;
-          const int id = isR ? v * BASE_LD + i + 1 : i * BASE_LD + min(v, i);
-          cacc[a][q] = T[id];
-          // the 8x8 block on the diagonal right after the panel belongs to warp 0; entries above the diagonal do not exist
+          const int id = isR ? v * BASE_LD + i + 1 : i * BASE_LD + v;
+          // the 8x8 block on the diagonal right after the panel belongs to warp 0; entries above the diagonal do not exist:
+          // both the load and the store of a masked entry go to this thread's private slot
           idx[a][q] = (isR || (v <= i && i >= r0 + 8)) ? id : DUMMY;
+          cacc[a][q] = T[idx[a][q]];
         }
       }
 #pragma unroll

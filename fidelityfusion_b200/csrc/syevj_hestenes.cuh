@@ -20,8 +20,8 @@
 // relative accuracy of tiny eigenvalues is not preserved (nor is it by syevd) and nothing downstream needs it
 // (A = kron(lambda) + 1/beta, hogp.py:173-177).
 //
-// Layout: P = ceil(n/2) "processors" = warps, 8 per CTA, CTAs of one matrix form a cluster of C = 1, 2, 4 or 8
-// (n <= 16, 32, 64, 128).  Tournament ordering of Brent & Luk: processor k holds (top_k, bot_k); after every step
+// Layout: P = ceil(n/2) "processors" = warps, 8 per CTA, CTAs of one matrix form a cluster of C = 2, 4 or 8
+// (n <= 32, 64, 128).  Tournament ordering of Brent & Luk: processor k holds (top_k, bot_k); after every step
 // top_0 stays, bot_0 -> top_1, top_k -> top_{k+1}, bot_k -> bot_{k-1}, top_{P-1} -> bot_{P-1}: all n (n-1) / 2 pairs
 // meet once per sweep of n - 1 steps, and every column moves to a NEIGHBOUR, so only the two boundary warps of a CTA
 // write into another CTA's shared memory.
@@ -390,8 +390,8 @@ syevj_hestenes_kernel(const double* __restrict__ Ain, int n, int C, double* __re
 inline int hj_cluster_size(int n) {
   const int P = (n + 1) / 2;
   const int need = (P + HJ_WARPS - 1) / HJ_WARPS;
-  int C = 1;
-  while (C < need) C *= 2;
+  int C = 2;            // at least 2: st.async (shared::cluster + remote mbarrier completion) needs a real cluster; for
+  while (C < need) C *= 2;   // n <= 16 the second CTA holds no processor and only takes part in the cluster barriers
   return C;
 }
 

@@ -452,6 +452,12 @@ def kernel_matrix(x1, x2, inv_ls, amp, clamp=False):
     return _KernelMatrix.apply(x1, x2, inv_ls, amp, clamp)
 
 
+def matmul(A, B):
+    """A @ B for 2-D fp64 CUDA operands on libffgp's DMMA mode-product kernel, autograd-aware (A @ B = B x_0 A)."""
+    from .tensorly_compat import mode_dot
+    return mode_dot(B, A, 0)
+
+
 # ---------------------------------------------------------------------------------------------
 # Cholesky factor + triangular inverse (for callers that want L itself)
 # ---------------------------------------------------------------------------------------------

@@ -560,6 +560,31 @@ def test_acquisition_scores_and_partials_match_reference_formulas(kind):
     assert float(vg.grad[5].abs().item()) == 0.0 or kind == 'UCB'
 
 
+@pytest.mark.parametrize('kind', ['UCB', 'EI', 'PI'])
+def test_acquisition_kernel_matches_the_reference_class_golden(kind):
+    """ffgp_acquisition_f64 (scores + partials in one launch) against the UNMODIFIED DiscreteAcquisitionFunction
+    (golden acq.npz from oracle/gen_golden_acq.py): UCB / PI at 1e-12, EI exactly reproduces the float32-rounded cdf/pdf
+    of the scipy round trip (DMF_acq.py:104) up to the last-ulp difference between erfc and scipy's ndtr."""
+    from fidelityfusion_b200.MF_BayesianOptimization.Discrete.DMF_acq import acquisition
+    g = load_golden('acq')
+    mu = G(g['mean']).requires_grad_(True)
+    v = G(g['var']).requires_grad_(True)
+    s = acquisition(mu, v, kind, f_best=float(g['f_best']), beta=0.2 * int(g['x_dimension']), xi=0.01)
+    s.sum().backward()
+    ref, dm, dv = g[kind + '_score'], g[kind + '_dmean'], g[kind + '_dvar']
+    ok = np.isfinite(ref).reshape(-1) & np.isfinite(dv).reshape(-1) & (g['var'].reshape(-1) > 1e-17)
+    # var <= 1e-18 sits on / below the clamp(std, 1e-9): PI is ~1e18 there and sqrt'(0) = inf in the reference's autograd
+    tol = 1e-12 if kind != 'EI' else 2e-7          # one float32 ulp of cdf/pdf where erfc and ndtr round differently
+    assert rel_err(s.detach().cpu().numpy().reshape(-1)[ok], ref.reshape(-1)[ok]) < tol
+    assert rel_err(mu.grad.cpu().numpy().reshape(-1)[ok], dm.reshape(-1)[ok]) < tol
+    assert rel_err(v.grad.cpu().numpy().reshape(-1)[ok], dv.reshape(-1)[ok]) < tol
+    # clamped region: same score (std = 1e-9), zero variance-gradient (torch.clamp passes no gradient below the bound)
+    lo = (g['var'].reshape(-1) < 1e-18) & np.isfinite(ref).reshape(-1)
+    if kind != 'UCB' and lo.any():
+        assert rel_err(s.detach().cpu().numpy().reshape(-1)[lo], ref.reshape(-1)[lo]) < 1e-9
+        assert float(np.abs(v.grad.cpu().numpy().reshape(-1)[lo]).max()) == 0.0
+
+
 def test_candidate_optimisation_step_on_device():
     """UCB/EI of the posterior differentiated w.r.t. the candidate through DiscreteAcquisitionFunction ->
     cigp.forward -> ffgp_dense_predict_bwd_f64, against the same composition on the CPU oracle."""

@@ -289,3 +289,19 @@ def test_posterior_gradient_wrt_test_points():
     x1, x2 = P(g['kx1']), P(g['kx2'])
     (O.ard_kernel(x1, x2, T(g['k_ls']), T(g['k_sv'])) * T(g['kW'])).sum().backward()
     assert rel_err(x1.grad, g['g_kx1']) < 1e-11 and rel_err(x2.grad, g['g_kx2']) < 1e-11
+
+
+@pytest.mark.parametrize('kind', ['UCB', 'EI', 'PI'])
+def test_acquisition_scores_pinned_on_the_reference_class(kind):
+    """O.acq_score against the unmodified DiscreteAcquisitionFunction (DMF_acq.py:49-128; golden from
+    oracle/gen_golden_acq.py), scores and autograd partials, including the float32-rounded cdf/pdf of EI (:104) and the
+    clamp(std, min=1e-9) region."""
+    g = load_golden('acq')
+    mu = T(g['mean']).requires_grad_(True)
+    v = T(g['var']).requires_grad_(True)
+    s = O.acq_score(mu, v, kind, f_best=float(g['f_best']), x_dimension=int(g['x_dimension']))
+    assert s.shape == g[kind + '_score'].shape
+    assert np.array_equal(s.detach().numpy(), g[kind + '_score'])           # same operations in the same order: bit-exact
+    s.sum().backward()
+    assert np.array_equal(mu.grad.numpy(), g[kind + '_dmean'])
+    assert np.array_equal(np.nan_to_num(v.grad.numpy(), nan=-7.0), np.nan_to_num(g[kind + '_dvar'], nan=-7.0))

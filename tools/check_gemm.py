@@ -26,7 +26,11 @@ for akm, bkm, kmode in itertools.product((1, 0), (1, 0), range(5)):
         if kmode in (2, 3) and N > K: continue
         if kmode in (1, 2, 3, 4) and (M != K or N != K) and lower_only: continue
         cases.append((akm, bkm, kmode, lower_only, batch, M, N, K, beta))
+SMALL = os.environ.get('FFGP_CHECK_SMALL') == '1'        # compute-sanitizer runs: same cases, batches cut to <= 12
 for akm, bkm, kmode, lower_only, batch, M, N, K, beta in cases:
+    if SMALL:
+        batch = min(batch, 12)
+        if M * N * K > 256 ** 3: continue
     A = torch.randn(batch, *((M, K) if akm else (K, M)), generator=g, dtype=torch.float64, device='cuda')
     Bm = torch.randn(batch, *((N, K) if bkm else (K, N)), generator=g, dtype=torch.float64, device='cuda')
     if kmode in (1, 4): A = torch.tril(A)
