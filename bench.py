@@ -210,6 +210,18 @@ def kron_numbers(torch):
         h.compute_loss(x, Y).backward()
 
     out['hogp_c4_loss_grad_ms'] = med(step) * 1e3
+    try:      # the same step as ONE CUDA-graph replay (+ fused Adam): what the device-side training loop costs per epoch
+        from fidelityfusion_b200.training import GraphedTrainer
+        h2 = HOGP({'fidelity_shapes': [torch.Size([32, 32, 16])]}).double().cuda()
+        tr = GraphedTrainer(lambda: h2.compute_loss(x, Y), h2.parameters(), lr=1e-3, history=64)
+        tr.run(3)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        tr.run(20, check=False)
+        torch.cuda.synchronize()
+        out['hogp_c4_graph_replay_ms_per_epoch'] = (time.perf_counter() - t0) / 20 * 1e3
+        tr.check()
+    except Exception as e:
+        out['hogp_c4_graph_replay_ms_per_epoch'] = repr(e)[:200]
     K = torch.exp(-0.5 * torch.cdist(x, x) ** 2)
     out['eigh_n128_ms'] = med(lambda: tl.eigh(K)) * 1e3
     out['eigh_n128_cusolver_ms'] = med(lambda: torch.linalg.eigh(K)) * 1e3        # the library kernel it replaces, same box
@@ -257,6 +269,14 @@ def reference_cuda_numbers(torch):
     roofline claim rides on these numbers; they are the library baseline beside ours, same box, same run."""
     from oracle import ff_oracle as O
     out = {'what': 'oracle port (the reference torch call sequence) on CUDA tensors: cuBLAS / cuSOLVER / autograd'}
+    torch.set_default_device('cuda')          # the reference builds torch.eye() / constants on the default device
+    try:
+        return _reference_cuda_body(torch, O, out)
+    finally:
+        torch.set_default_device('cpu')
+
+
+def _reference_cuda_body(torch, O, out):
 
     def timed(fn, reps):
         fn(); torch.cuda.synchronize()
@@ -268,7 +288,9 @@ def reference_cuda_numbers(torch):
         return e0.elapsed_time(e1) / reps
 
     # C2: one NLL + gradient evaluation, N = 8192, d = 16
-    x, y = [t.cuda() for t in c2_inputs(torch)]
+    with torch.device('cpu'):
+        xc_, yc_ = c2_inputs(torch)
+    x, y = xc_.cuda(), yc_.cuda()
     ls, sv, lb = (torch.ones(D_C2, device='cuda'), torch.ones(1, device='cuda'), torch.ones(1, device='cuda'))
     ms = timed(lambda: O.cigp_ard_nll_and_grads(x, y, ls, sv, lb), 3)
     out['c2_ms_per_eval'] = ms
@@ -276,7 +298,9 @@ def reference_cuda_numbers(torch):
     del x, y
     torch.cuda.empty_cache()
     # C5: 64 of the 4096 problems, sequentially like the reference's Python loops (v1/CFKG.py:124-129)
-    bx, by, bls, bsv, blb, bxs = [t.cuda() for t in c5_inputs(torch, 0, 64)]
+    with torch.device('cpu'):
+        c5 = c5_inputs(torch, 0, 64)
+    bx, by, bls, bsv, blb, bxs = [t.cuda() for t in c5]
 
     def c5_loop():
         for b in range(64):
@@ -298,9 +322,11 @@ def reference_cuda_numbers(torch):
     out['c5_gps_per_s_torch_batched_nll_grad_only'] = 64 / ms * 1e3
     del bx, by
     # C4: one HOGP loss + gradient, 128 x 32 x 32 x 16 (eigh through cuSOLVER syevd, autograd through it)
-    g = torch.Generator().manual_seed(4)
-    xk = torch.rand(128, 5, generator=g, dtype=torch.float64).cuda()
-    Y = torch.randn(128, 32, 32, 16, generator=g, dtype=torch.float64).cuda()
+    with torch.device('cpu'):
+        g = torch.Generator().manual_seed(4)
+        xk = torch.rand(128, 5, generator=g, dtype=torch.float64)
+        Y = torch.randn(128, 32, 32, 16, generator=g, dtype=torch.float64)
+    xk, Y = xk.cuda(), Y.cuda()
     grids = [xk] + [torch.arange(s_, dtype=torch.float64, device='cuda').reshape(-1, 1) for s_ in (32, 32, 16)]
 
     def hogp():

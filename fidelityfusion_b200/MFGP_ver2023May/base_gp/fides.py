@@ -55,8 +55,8 @@ class FIDES(torch.nn.Module):
             mean, var = ops.dense_predict(self.train_x, self.train_y, x, inv_ls, amp,
                                           diag_add=(noise_inv + JITTER).reshape(1), cov_offset=noise_inv,
                                           full_cov=False, clamp=clamp, cache=self.factor_cache,
-                                          cache_token=ops.state_token(self, self.train_x, self.train_y)
-                                          + (self.l1, self.h1, self.l2, self.h2))
+                                          cache_token=(ops.state_token(self, self.train_x, self.train_y),
+                                                       self.l1, self.h1, self.l2, self.h2))
         return mean, var.view(-1, 1)
 
     def compute_loss(self, x, y, x_var=0., y_var=0., update_data=False):

@@ -72,17 +72,39 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     B.check(rc, 'ffgp_dense_fit_f64')
     if check:
         ops.check_info(info)
-    out = {'nll': nll + 0.5 * n * D * math.log(2 * PI)}
-    if not check:
-        out['info'] = info.to(torch.float64)
-    if want_grad:
-        out['g_length_scales'] = g_il * (-1.0 / (ell * ell)) * torch.sign(ls)       # inv_ls = 1/(|ls|+eps)
-        out['g_signal_variance'] = g_amp * torch.sign(sv)                           # amp = |sv|
-        out['g_log_beta'] = g_diag.sum(1) * (-noise)                                # diag = e^-lb + jitter
-    if ns:
-        out['mean'] = mean
-        out['var'] = var
+    # ONE launch writes the packed result rows: NLL constant, chain rule to the raw parameters, predictions and (for the
+    # asynchronous mode) the status column.  The dict entries below are views of that buffer; sharded_cigp_eval ships
+    # the buffer itself through its single all-gather.
+    keys, widths = result_layout(d, D, ns, want_grad, check)
+    ld = sum(widths)
+    packed = torch.empty(Bn, ld, dtype=torch.float64, device=dev)
+    rc = L.ffgp_batched_pack_f64(B.ptr(nll), B.ptr(g_il), B.ptr(g_amp), B.ptr(g_diag), B.ptr(mean), B.ptr(var), B.ptr(info),
+                                 B.ptr(ls), B.ptr(sv), B.ptr(lb), Bn, n, d, D, ns, int(want_grad), int(not check),
+                                 0.5 * n * D * math.log(2 * PI), EPS, B.ptr(packed), ld, B.stream_ptr())
+    B.check(rc, 'ffgp_batched_pack_f64')
+    out = unpack_results(packed, result_shapes(d, D, ns), keys)
+    out['_packed'] = packed
     return out
+
+
+def result_layout(d, D, ns, want_grad, check):
+    """(keys, column widths) of a packed result row, in the order ffgp_batched_pack_f64 writes them."""
+    keys, widths = ['nll'], [1]
+    if want_grad:
+        keys += ['g_length_scales', 'g_signal_variance', 'g_log_beta']
+        widths += [d, 1, 1]
+    if ns:
+        keys += ['mean', 'var']
+        widths += [ns * D, ns]
+    if not check:
+        keys.append('info')
+        widths.append(1)
+    return keys, widths
+
+
+def result_shapes(d, D, ns):
+    return {'nll': (), 'g_length_scales': (d,), 'g_signal_variance': (), 'g_log_beta': (), 'mean': (ns, D), 'var': (ns,),
+            'info': ()}
 
 
 def empty_result(d, D, ns, want_grad, check, device):
@@ -146,7 +168,7 @@ def sharded_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
         res = empty_result(x.shape[2], y.shape[2], 0 if xs is None else xs.shape[1], want_grad, check, x.device)
     keys = [k for k in ('nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var', 'info') if k in res]
     shapes = {k: tuple(res[k].shape[1:]) for k in keys}
-    local = pack_results(res, keys)
+    local = res['_packed'] if '_packed' in res else pack_results(res, keys)      # the CUDA path packs in its own kernel
     counts = [shard_range(Bn, r, world) for r in range(world)]
     cmax = max(c[1] - c[0] for c in counts)
     if local.shape[0] < cmax:            # ragged split: pad to the largest block so ONE fixed-size collective suffices

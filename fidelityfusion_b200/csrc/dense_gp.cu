@@ -14,6 +14,7 @@
 #include "acq_kernels.cuh"
 #include "train_kernels.cuh"
 #include "match_kernels.cuh"
+#include "pack_kernels.cuh"
 
 namespace ffgp {
 
@@ -1088,6 +1089,28 @@ int ffgp_adam_step_f64(void* const* table, const int* sizes, int ntensors, doubl
     return fail(-2, "ffgp_adam_step_f64: bad hyper-parameter");
   adam_step_kernel<<<ntensors, 256, 0, (cudaStream_t)stream>>>(table, sizes, lr, beta1, beta2, eps, maximize, loss, loss_hist,
                                                              loss_hist ? hist_cap : 0);
+  FFGP_LAUNCHED();
+  return 0;
+}
+
+int ffgp_batched_pack_f64(const double* nll_core, const double* g_inv_ls, const double* g_amp, const double* g_diag,
+                          const double* mean, const double* var, const int* info, const double* length_scales,
+                          const double* signal_variance, const double* log_beta, int batch, int n, int d, int D, int ns,
+                          int want_grad, int with_info, double nll_const, double eps, double* out, int ld_out, void* stream) {
+  if (!nll_core || !out) return fail(-1, "ffgp_batched_pack_f64: null pointer");
+  if (want_grad && (!g_inv_ls || !g_amp || !g_diag || !length_scales || !signal_variance || !log_beta))
+    return fail(-1, "ffgp_batched_pack_f64: gradient inputs missing");
+  if (ns > 0 && (!mean || !var)) return fail(-1, "ffgp_batched_pack_f64: prediction inputs missing");
+  if (with_info && !info) return fail(-1, "ffgp_batched_pack_f64: info missing");
+  if (batch <= 0 || n <= 0 || d < 0 || D <= 0 || ns < 0) return fail(-2, "ffgp_batched_pack_f64: bad size");
+  const int need = 1 + (want_grad ? d + 2 : 0) + (ns > 0 ? ns * D + ns : 0) + (with_info ? 1 : 0);
+  if (ld_out < need) return fail(-2, "ffgp_batched_pack_f64: ld_out too small");
+  PackParams p;
+  p.nll_core = nll_core; p.g_il = g_inv_ls; p.g_amp = g_amp; p.g_diag = g_diag; p.mean = mean; p.var = var; p.info = info;
+  p.ls = length_scales; p.sv = signal_variance; p.lb = log_beta;
+  p.B = batch; p.n = n; p.d = d; p.D = D; p.ns = ns; p.want_grad = want_grad; p.with_info = with_info;
+  p.nll_const = nll_const; p.eps = eps; p.out = out; p.ld = ld_out;
+  pack_results_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(p);
   FFGP_LAUNCHED();
   return 0;
 }

@@ -172,6 +172,19 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
                        double* out_mean, double* out_cov, int* info, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Packed result rows of a batch of cigp + ARDKernel problems (the buffer ONE all-gather ships):
+ *   out[b] = [ nll | d/d length_scales [d] | d/d signal_variance | d/d log_beta | mean [ns*D] | var [ns] | info ]
+ * from the outputs of ffgp_dense_fit_f64 (nll_core, g_inv_ls, g_amp, g_diag, mean, diagonal var, info).  The chain rule to
+ * the reference's raw parameters (inv_ls = 1/(|length_scales| + eps), amp = |signal_variance|, diag = e^-log_beta + jitter:
+ * GaussianProcess/kernel.py:100-105, cigp_v10.py:57-58) and nll = nll_core + nll_const are applied in the same launch.
+ * The gradient block is present iff want_grad, the prediction block iff ns > 0, the status column iff with_info.
+ * --------------------------------------------------------------------------------------- */
+int ffgp_batched_pack_f64(const double* nll_core, const double* g_inv_ls, const double* g_amp, const double* g_diag,
+                          const double* mean, const double* var, const int* info, const double* length_scales,
+                          const double* signal_variance, const double* log_beta, int batch, int n, int d, int D, int ns,
+                          int want_grad, int with_info, double nll_const, double eps, double* out, int ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Subset / overlap matching of two fidelities' inputs: match[i] = smallest j with b[j][:] == a[i][:]
  * under IEEE equality (NaN matches nothing, -0.0 == 0.0), else -1.  a [na][d], b [nb][d], match int[na].
  * Replaces the [na][nb][d] broadcast compare of FidelityFusion_Models/MF_data.py:199-202 / 235-238
