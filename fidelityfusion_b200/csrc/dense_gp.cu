@@ -237,6 +237,12 @@ static DenseWs layout_ws(int n, int d, int D, int ns, int batch, char* base) {
     const long long bt = std::max(batch, 1);
     const long long nchunks = (bt + chunk - 1) / chunk;
     w.chunk = (int)((bt + nchunks - 1) / nchunks);
+    // ... and whole waves: a third of the launches of a batched evaluation have ONE CTA per problem (base blocks, 128-level
+    // products), so a chunk of 820 problems is 5.54 waves on 148 SMs = 6 rounds.  Prefer the largest multiple of the SM
+    // count that fits when it does not add a chunk (4096 problems: 4 x 888 + 544 = 28 rounds instead of 5 x 820 = 30).
+    const long long sms = 148;
+    const long long whole = chunk / sms * sms;
+    if (nchunks > 1 && whole >= sms && (bt + whole - 1) / whole <= nchunks) w.chunk = (int)whole;
   }
   size_t off = 0;
   auto take = [&](size_t nbytes) {
@@ -608,6 +614,8 @@ static cudaError_t ensure_attrs() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N_BATCHED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(symv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 1024 * (int)sizeof(double));
+  if (e != cudaSuccess) return e;
   for (auto kern : {grad_contract_kernel<false>, grad_contract_kernel<true>}) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem_doubles(GRAD_DMAX) * 8);
     if (e != cudaSuccess) return e;
@@ -795,10 +803,28 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
     const int nb = std::min(w.chunk, batch - b0);
     g_persist = nb >= 8;      // same rule as the look-ahead switch: a large batch fills the machine by itself
     int rc;
+    // Batched gradient evaluations need S = Sigma^-1 anyway: alpha = S y in ONE pass over S (symv_lower_kernel) replaces
+    // Gamma = M y and alpha = M^T Gamma (two passes over M) and y^T alpha gives the quadratic form.  FFGP_SYMV=0: old path.
+    static int symv_on = -1;
+    if (symv_on < 0) { const char* e = getenv("FFGP_SYMV"); symv_on = (e && atoi(e) == 0) ? 0 : 1; }
+    const bool use_symv = symv_on && want_grad && !reuse_factor && !w.gemm_rhs && nb >= 8 && w.np <= 1024 &&
+                          debug_stop_after() == 0;
     if (!reuse_factor) {
       if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
       if (debug_stop_after() == 1 || debug_stop_after() == 2) continue;
-      if ((rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
+      if (!use_symv && (rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
+    }
+    if (use_symv) {
+      FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
+      const long long sG = (long long)w.np * D;
+      symv_lower_kernel<<<dim3(nb, D), 256, (size_t)9 * w.np * sizeof(double), st>>>(
+          w.A, w.np, sM, n, w.np, y + (long long)b0 * n * D, D, (long long)n * D, w.alpha, sG, w.rowsq);
+      FFGP_LAUNCHED();
+      if (D > 1) {
+        rowdot_kernel<<<dim3((w.np + 255) / 256, nb), 256, 0, st>>>(y + (long long)b0 * n * D, (long long)n * D, w.alpha, sG, n,
+                                                                     w.np, D, w.rowsq);
+        FFGP_LAUNCHED();
+      }
     }
     if (want_nll) {
       nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, D, out_nll + b0,
@@ -808,7 +834,8 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
     if (!reuse_factor && (rc = copy_alpha_out(a, w, b0, nb, out_alpha, st)) != 0) return rc;
     if (want_grad) {
       // S = M^T M (lower) into the dead A buffer
-      FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
+      if (!use_symv)
+        FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
       if (debug_stop_after() == 3) continue;
       int src_is_G = 0;
       if (w.gemm_rhs) {   // G = 0.5 (D S - alpha alpha^T) through the GEMM epilogue

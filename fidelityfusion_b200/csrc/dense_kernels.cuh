@@ -633,6 +633,77 @@ __global__ void __launch_bounds__(256) colsum_weighted_kernel(const double* __re
 }
 
 // nll[b] = 0.5 * sum_i rowsq[i] + D * sum_k logdet_part[k]      (fixed-order tree)
+// ------------------------------------------------------------------------------------------
+// alpha = S y from the LOWER triangle of S = Sigma^-1 (what the S = M^T M launch leaves in the workspace), one CTA per
+// (problem, right-hand-side column).  Batched gradient evaluations compute S anyway; alpha = S y in ONE pass over
+// S (8 N^2 / 2 bytes) replaces Gamma = M y and alpha = M^T Gamma (two passes over M by two kernels), and
+// ||Gamma||^2 = y^T alpha gives the quadratic form: rowsq[i] = y_i alpha_i summed by nll_reduce_kernel as before.
+// 32 x 32 tiles of the lower triangle, round-robin over the 8 warps; a lane holds column l of the tile (32 independent
+// coalesced 256-byte row loads in flight), the tile's contribution to alpha[rows] is a warp reduction per row, the
+// mirrored contribution to alpha[cols] is lane-local.  Per-warp partial vectors in shared memory, summed in fixed order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) symv_lower_kernel(const double* __restrict__ S, int ld, long long sS, int n, int np,
+                                                         const double* __restrict__ y, int D, long long sy,
+                                                         double* __restrict__ alpha, long long salpha,
+                                                         double* __restrict__ rowsq) {
+  extern __shared__ __align__(16) double sv_sm[];            // [8][np] per-warp partial alpha, then [np] y column
+  const int b = blockIdx.x, col = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* part = sv_sm + (size_t)warp * np;
+  double* ysh = sv_sm + (size_t)8 * np;
+  const double* Sb = S + (long long)b * sS;
+  for (int i = tid; i < np; i += 256) ysh[i] = (i < n) ? y[(long long)b * sy + (long long)i * D + col] : 0.0;
+  for (int i = lane; i < np; i += 32) part[i] = 0.0;
+  __syncthreads();
+  const int nt = (n + 31) >> 5;                              // tile rows / columns that hold data
+  const int ntiles = nt * (nt + 1) / 2;
+  for (int t = warp; t < ntiles; t += 8) {
+    int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int i0 = ti * 32, j0 = tj * 32;
+    const bool diag = ti == tj;
+    double v[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++) v[r] = Sb[(long long)(i0 + r) * ld + j0 + lane];
+    const double yc = ysh[j0 + lane];
+    double colacc = 0.0;
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+      // element (i0 + r, j0 + lane): on a diagonal tile only r >= lane exists; its mirror (r > lane) feeds alpha[j0 + lane]
+      const bool lower = !diag || r >= lane;
+      double rowc = lower ? v[r] * yc : 0.0;
+      if (lower && (!diag || r > lane)) colacc = fma(v[r], ysh[i0 + r], colacc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rowc += __shfl_xor_sync(0xffffffffu, rowc, o);
+      if (lane == 0) part[i0 + r] += rowc;
+    }
+    __syncwarp();
+    part[j0 + lane] += colacc;
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = tid; i < np; i += 256) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) a += sv_sm[(size_t)w * np + i];
+    if (i >= n) a = 0.0;
+    alpha[(long long)b * salpha + (long long)i * D + col] = a;
+    if (D == 1) rowsq[(long long)b * np + i] = a * ysh[i];
+  }
+}
+
+// rowsq[i] = sum_c y[i][c] alpha[i][c] for D > 1 (the per-column symv launches above cannot combine columns)
+__global__ void __launch_bounds__(256) rowdot_kernel(const double* __restrict__ y, long long sy, const double* __restrict__ alpha,
+                                                     long long salpha, int n, int np, int D, double* __restrict__ rowsq) {
+  const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= np) return;
+  double a = 0.0;
+  if (i < n)
+    for (int c = 0; c < D; c++) a = fma(y[(long long)b * sy + (long long)i * D + c], alpha[(long long)b * salpha + (long long)i * D + c], a);
+  rowsq[(long long)b * np + i] = a;
+}
+
 __global__ void __launch_bounds__(256) nll_reduce_kernel(const double* __restrict__ rowsq, int np,
                                                          const double* __restrict__ logdet_part, int nblk, int D,
                                                          double* __restrict__ nll, double* __restrict__ logdet_out) {
