@@ -175,7 +175,16 @@ static cudaError_t gemm(bool a_kmaj, bool b_kmaj, const double* A, int lda, long
   cudaError_t e = cudaErrorNotSupported;
   int persistent_ctas = (persist_mode() == 2 || (g_persist && persist_mode() == 1 && (!lower_only || persist_lower()))) ? num_sms() : 0;
   if (g_reserve_sms > 0 && g_reserve_sms < num_sms()) persistent_ctas = num_sms() - g_reserve_sms;
-  if (big && use_tma_gemm()) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st, persistent_ctas);
+  // 128 x 64 tiles with two CTAs per SM (gemm_tma.cuh TgCfg<2>): the short-K products of batched problems (a tile's
+  // hand-over is 15-25 % of a 128/256-deep tile and one CTA per SM cannot hide it) and 64-wide right-hand sides.
+  // FFGP_GEMM_N64: 0 never, 1 (default) batched non-lower launches with K <= 1024 and N % 128 != 0 shapes, 2 every eligible launch.
+  static int n64 = -1;
+  if (n64 < 0) { const char* ev = getenv("FFGP_GEMM_N64"); n64 = ev ? atoi(ev) : 1; }
+  const bool narrow_ok = use_tma_gemm() && !lower_only && M % 128 == 0 && N % 64 == 0 && K % 16 == 0 &&
+                         (long long)(M / 128) * (N / 64) * batch >= 2LL * num_sms();
+  const bool narrow = narrow_ok && (n64 == 2 || (n64 == 1 && ((g_persist && K <= 1024) || N % 128 != 0)));
+  if (narrow) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st, persistent_ctas, true);
+  if (e == cudaErrorNotSupported && big && use_tma_gemm()) e = launch_gemm_tma(a_kmaj, b_kmaj, p, batch_outer, st, persistent_ctas);
   if (e == cudaErrorNotSupported) {
     if (a_kmaj && b_kmaj) e = launch_gemm<true, true>(p, batch, big, st);
     else if (a_kmaj && !b_kmaj) e = launch_gemm<true, false>(p, batch, big, st);
@@ -271,6 +280,18 @@ static DenseWs layout_ws(int n, int d, int D, int ns, int batch, char* base) {
   }
   w.bytes = off + 256;
   return w;
+}
+
+// The same layout advanced by k problems (every array is [chunk][...]): the slice a second stream works on.
+static DenseWs ws_offset(const DenseWs& w, int k, int d, int D) {
+  DenseWs r = w;
+  const size_t np = w.np, nsp = w.nsp, Dw = w.gemm_rhs ? w.Dp : D, kk = (size_t)k;
+  r.A += kk * np * np; r.L += kk * np * np; r.M += kk * np * np;
+  r.Gm += kk * np * Dw; r.alpha += kk * np * Dw;
+  if (r.Ypad) r.Ypad += kk * np * w.Dp;
+  r.rowsq += kk * np; r.logdet_part += kk * w.nblk; r.partial += kk * w.ngtile * (d + 1);
+  if (w.nsp) { r.Kx += kk * np * nsp; r.V += kk * np * nsp; r.Kxx += kk * nsp * nsp; r.colsq += kk * nsp; r.meanp += kk * nsp * w.Dp; }
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -799,9 +820,8 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
   if (!reuse_factor) FFGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
   const long long sM = (long long)w.np * w.np;
   struct PersistGuard { ~PersistGuard() { g_persist = 0; } } persist_guard;
-  for (int b0 = 0; b0 < batch; b0 += w.chunk) {
-    const int nb = std::min(w.chunk, batch - b0);
-    g_persist = nb >= 8;      // same rule as the look-ahead switch: a large batch fills the machine by itself
+  // One chunk (problems [b0, b0 + nb) in the workspace slice `w`) on stream `st`.
+  auto run_chunk = [&](int b0, int nb, const DenseWs& w, cudaStream_t st) -> int {
     int rc;
     // Batched gradient evaluations need S = Sigma^-1 anyway: alpha = S y in ONE pass over S (symv_lower_kernel) replaces
     // Gamma = M y and alpha = M^T Gamma (two passes over M) and y^T alpha gives the quadratic form.  FFGP_SYMV=0: old path.
@@ -811,7 +831,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
                           debug_stop_after() == 0;
     if (!reuse_factor) {
       if ((rc = assemble_and_factor(a, w, b0, nb, info, st)) != 0) return rc;
-      if (debug_stop_after() == 1 || debug_stop_after() == 2) continue;
+      if (debug_stop_after() == 1 || debug_stop_after() == 2) return 0;
       if (!use_symv && (rc = solve_rhs(a, w, b0, nb, st)) != 0) return rc;
     }
     if (use_symv) {
@@ -836,7 +856,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
       // S = M^T M (lower) into the dead A buffer
       if (!use_symv)
         FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.M, w.np, sM, w.A, w.np, sM, w.np, w.np, w.np, 1.0, 0.0, 1, K_GE_ROW, nb, st));
-      if (debug_stop_after() == 3) continue;
+      if (debug_stop_after() == 3) return 0;
       int src_is_G = 0;
       if (w.gemm_rhs) {   // G = 0.5 (D S - alpha alpha^T) through the GEMM epilogue
         const long long sG = (long long)w.np * w.Dp;
@@ -865,7 +885,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
         FFGP_LAUNCHED();
       }
     }
-    if (!want_pred) continue;
+    if (!want_pred) return 0;
     // ---------------- posterior at xs, from the factor that is still resident (M, alpha) ----------------
     const long long sKx = (long long)w.np * w.nsp, sKxx = (long long)w.nsp * w.nsp;
     KernelMatrixParams kp;
@@ -898,7 +918,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
                                            (long long)ns * D);
       FFGP_LAUNCHED();
     }
-    if (!out_cov) continue;
+    if (!out_cov) return 0;
     // V = M Kx
     FFGP_CUDA(gemm(true, false, w.M, w.np, sM, w.Kx, w.nsp, sKx, w.V, w.nsp, sKx, w.np, w.nsp, w.np, 1.0, 0.0, 0, K_LE_ROW,
                    nb, st));
@@ -932,6 +952,32 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
                                                                   cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr,
                                                                   params_batched ? 1 : 0, out_cov + (long long)b0 * ns, ns, w.nsp);
       FFGP_LAUNCHED();
+    }
+    return 0;
+  };
+  // Experiment (FFGP_SPLIT=1, default off): the two halves of a chunk on TWO streams, so that the ramp-up / drain of the
+  // ~30 dependent launches of one half (~11 us per launch, profiles/r02_gemm_small_k_tiles.txt) is filled by the other
+  // half's CTAs.  Measured on BASELINE config 5: 41.56 ms per sweep against 41.07 ms on one stream
+  // (profiles/r02_c5_experiments.txt) - every GEMM CTA owns a whole SM, so the second chain only ever gets the SMs the
+  // first one has drained, and each half has half as many waves to amortise its own launches over.
+  static int split_on = -1;
+  if (split_on < 0) { const char* e = getenv("FFGP_SPLIT"); split_on = (e && atoi(e) == 1) ? 1 : 0; }
+  for (int b0 = 0; b0 < batch; b0 += w.chunk) {
+    const int nb = std::min(w.chunk, batch - b0);
+    g_persist = nb >= 8;      // same rule as the look-ahead switch: a large batch fills the machine by itself
+    int rc;
+    AuxStream* aux = nullptr;
+    if (split_on && !reuse_factor && nb >= 4 * num_sms() && debug_stop_after() == 0 && get_aux(&aux) == cudaSuccess) {
+      const int sms = num_sms();
+      const int na = std::min(nb - sms, (nb / 2 + sms - 1) / sms * sms);          // first half, whole waves
+      FFGP_CUDA(cudaEventRecord(aux->ev_fork, st));
+      FFGP_CUDA(cudaStreamWaitEvent(aux->st_bulk, aux->ev_fork, 0));
+      if ((rc = run_chunk(b0, na, w, st)) != 0) return rc;
+      if ((rc = run_chunk(b0 + na, nb - na, ws_offset(w, na, d, D), aux->st_bulk)) != 0) return rc;
+      FFGP_CUDA(cudaEventRecord(aux->ev_join, aux->st_bulk));
+      FFGP_CUDA(cudaStreamWaitEvent(st, aux->ev_join, 0));
+    } else {
+      if ((rc = run_chunk(b0, nb, w, st)) != 0) return rc;
     }
   }
   return 0;

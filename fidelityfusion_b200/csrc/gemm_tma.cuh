@@ -39,6 +39,27 @@ constexpr int TG_STAGE_BYTES = 2 * TG_PANEL_BYTES;
 constexpr int TG_TILE_RING = 8;                                         // > TG_STAGES: the producer is at most TG_STAGES tiles ahead
 constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/ + 4 * TG_TILE_RING;
 
+// Tile shape by the number of warp COLUMNS WN (warp tile 64 x 32 either way, same per-warp code and register budget):
+//   WN = 4: 128 x 128 tile, 8 MMA warps + producer warpgroup = 384 threads, 6 x 32 KB stages, ONE CTA per SM
+//           (168 registers at launch, setmaxnreg 40 / 232).  Long-K tiles: 0.99 of the DGEMM rate at K = 8192.
+//   WN = 2: 128 x 64 tile, 4 MMA warps + producer warpgroup = 256 threads, 4 x 24 KB stages, TWO CTAs per SM
+//           (128 registers at launch, setmaxnreg 24 / 232): the tile hand-over of one CTA (epilogue stores, decode,
+//           accumulator init, first barrier) hides behind the other CTA's DMMAs.  For the 128/256-deep tiles of the
+//           batched factorisation, where that hand-over is 15-25 % of a tile (profiles/r02_gemm_small_k_tiles.txt),
+//           and for 64-wide right-hand sides (the posterior's V = M K*).  Not for lower_only launches (square tiles).
+template <int WN>
+struct TgCfg {
+  static constexpr int BN = 32 * WN;
+  static constexpr int CW = 2 * WN;                                     // MMA warps
+  static constexpr int THREADS = (CW + 4) * 32;
+  static constexpr int STAGES = WN == 4 ? TG_STAGES : 4;
+  static constexpr int B_PANEL_BYTES = BN * TG_BK * 8;
+  static constexpr int STAGE_BYTES = TG_PANEL_BYTES + B_PANEL_BYTES;
+  static constexpr int REGS_PRODUCER = WN == 4 ? TG_REGS_PRODUCER : 24;
+  static constexpr int CTAS_PER_SM = WN == 4 ? 1 : 2;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 128 + 4 * TG_TILE_RING;
+};
+
 struct TmaGemmParams {
   double* C;
   int ldc;
@@ -103,11 +124,12 @@ struct TgLive {
 // gemm_dmma_kernel).  Items are numbered tile-fastest, so the tiles of one problem are in flight together and share
 // their operand panels through L2.
 struct TgTile { int ti, tj, k_lo, k_hi, zo, zi; };
+template <int BN>
 __device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int w) {
   TgTile r;
   const int z = w / p.tiles;
   int t = w - z * p.tiles;
-  const int tiles_m = p.M / TG_BM, tiles_n = p.N / TG_BN;
+  const int tiles_m = p.M / TG_BM, tiles_n = p.N / BN;
   if (p.lower_only) {
     if (p.heavy_first && p.kmode != K_GE_ROW) t = p.tiles - 1 - t;
     r.ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
@@ -119,10 +141,10 @@ __device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int w) {
     if (p.kmode == K_LE_COL || p.kmode == K_GE_COL) { r.tj = t / tiles_m; r.ti = t - r.tj * tiles_m; }
     else { r.ti = t / tiles_n; r.tj = t - r.ti * tiles_n; }
   }
-  const int i0 = r.ti * TG_BM, j0 = r.tj * TG_BN;
+  const int i0 = r.ti * TG_BM, j0 = r.tj * BN;
   r.k_lo = 0; r.k_hi = p.K;
   if (p.kmode == K_LE_ROW) r.k_hi = min(p.K, i0 + TG_BM);
-  else if (p.kmode == K_LE_COL) r.k_hi = min(p.K, j0 + TG_BN);
+  else if (p.kmode == K_LE_COL) r.k_hi = min(p.K, j0 + BN);
   else if (p.kmode == K_GE_COL) r.k_lo = j0;
   else if (p.kmode == K_GE_ROW) r.k_lo = i0;
   r.zo = z / p.inner; r.zi = z - r.zo * p.inner;
@@ -130,9 +152,11 @@ __device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int w) {
 }
 
 // A_KMAJ: A(i,p) = A[i*lda + p]  else  A(i,p) = A[p*lda + i];   B_KMAJ: B(p,j) = B[j*ldb + p]  else  B[p*ldb + j]
-template <bool A_KMAJ, bool B_KMAJ>
-__global__ void __launch_bounds__(TG_THREADS, 1)
+template <bool A_KMAJ, bool B_KMAJ, int WN = 4>
+__global__ void __launch_bounds__(TgCfg<WN>::THREADS, TgCfg<WN>::CTAS_PER_SM)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaGemmParams p) {
+  using Cfg = TgCfg<WN>;
+  constexpr int TG_BN = Cfg::BN, TG_STAGES = Cfg::STAGES, TG_STAGE_BYTES = Cfg::STAGE_BYTES, TG_CONSUMER_WARPS = Cfg::CW;
   extern __shared__ unsigned char tg_smem_raw[];
   const uint32_t smem_base = (tg_smem_u32(tg_smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B panels need 1024-B alignment
   const uint32_t bar_base = smem_base + TG_STAGES * TG_STAGE_BYTES;           // full[s] at +8s, empty[s] at +64+8s
@@ -151,7 +175,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   if (warp >= TG_CONSUMER_WARPS) {
     // ===================== TMA producer warpgroup (one elected lane works) =====================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TG_REGS_PRODUCER));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_PRODUCER));
     if (warp == TG_CONSUMER_WARPS && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -164,7 +188,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       for (int n = 0;; n++) {
         unsigned int fetched = 0;
         if (p.sched) fetched = atomicAdd(p.sched, 1u);      // next item, requested before this one's loads are issued
-        const TgTile tl = tg_decode(p, w);
+        const TgTile tl = tg_decode<TG_BN>(p, w);
         const int i0 = tl.ti * TG_BM, j0 = tl.tj * TG_BN;
         const int KT = (tl.k_hi - tl.k_lo) / TG_BK;
         for (int kt = 0; kt < KT; kt++, it++) {
@@ -205,7 +229,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   // the same share of any triangular region of the tile, so structural zeros (below) can be skipped without one warp
   // becoming the straggler.  Warps w and w + 4 share an SM sub-partition: wn is mirrored in the second warp row so the
   // sub-partitions' DMMA counts on a symmetric diagonal tile are 36/32/36/32 of 64.
-  const int wm = warp >> 2, wn = (warp & 3) ^ (wm ? 3 : 0);
+  const int wm = warp / WN, wn = (warp % WN) ^ (wm ? WN - 1 : 0);
   const int g = lane >> 2, tq = lane & 3;
   constexpr int MT = 8, NT = 4;
   // per-thread fragment offsets inside a stage (bytes)
@@ -222,7 +246,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < MT; i++) af[buf][i] = tg_lds(pa + i * 2048);
 #pragma unroll
-    for (int j = 0; j < NT; j++) bf[buf][j] = tg_lds(pb + j * 4096);
+    for (int j = 0; j < NT; j++) bf[buf][j] = tg_lds(pb + j * (WN * 1024));
   };
 
   const double alpha = p.alpha, beta = p.beta;
@@ -233,7 +257,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   int it0 = 0;                                     // k-steps consumed before this tile (the stage ring runs on across tiles)
   int w = blockIdx.x;
   for (int n = 0;; n++) {
-  const TgTile tl = tg_decode(p, w);
+  const TgTile tl = tg_decode<TG_BN>(p, w);
   const int ti = tl.ti, tj = tl.tj, i0 = ti * TG_BM, j0 = tj * TG_BN, k_hi = tl.k_hi;
   const int KT = (tl.k_hi - tl.k_lo) / TG_BK;
   // ---- structural zeros.  A kmode says an operand is TRIANGULAR (ffgp.h): besides shortening the K range of the tile,
@@ -258,7 +282,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const int row = i0 + (2 * i + wm) * 8 + g;
 #pragma unroll
       for (int j = 0; j < NT; j++) {
-        const int col = j0 + (4 * j + wn) * 8 + tq * 2;
+        const int col = j0 + (WN * j + wn) * 8 + tq * 2;
         double2 o = make_double2(0.0, 0.0);
         if (2 * i + wm - 4 * j - wn >= sym_thr) o = *reinterpret_cast<const double2*>(Cg + (long long)row * p.ldc + col);
         acc[i][j][0] = r * o.x;
@@ -328,7 +352,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     int variant = 0;
     if (sym_diag) {
       variant = 21 + role;
-    } else if (tri_mode != 0 && kt >= tri_kt0 && kt < tri_kt0 + TG_BM / TG_BK) {
+    } else if (tri_mode != 0 && kt >= tri_kt0 && kt < tri_kt0 + ((tri_mode == 1 || tri_mode == 4) ? TG_BM : TG_BN) / TG_BK) {
       const int pk = (kt - tri_kt0) * TG_BK;             // first k of the step inside the diagonal K block
       if (tri_mode == 1) {                               // (2 i + wm) * 8 + 7 >= pk
         const int lo = min(MT - 1, (pk - 7 - 8 * wm + 15) >> 4);
@@ -337,10 +361,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int hi = max(1, ((pk + 15 - 8 * wm) >> 4) + 1);
         if (hi < MT) variant = 7 + hi;
       } else if (tri_mode == 2) {                        // (4 j + wn) * 8 + 7 >= pk
-        const int lo = min(NT - 1, (pk - 7 - 8 * wn + 31) >> 5);
+        const int lo = min(NT - 1, (pk - 7 - 8 * wn + 8 * WN - 1) / (8 * WN));
         if (lo > 0) variant = 14 + lo;
       } else {                                           // (4 j + wn) * 8 <= pk + 15
-        const int hi = max(1, ((pk + 15 - 8 * wn) >> 5) + 1);
+        const int hi = max(1, (pk + 15 - 8 * wn) / (8 * WN) + 1);
         if (hi < NT) variant = 17 + hi;
       }
     }
@@ -384,7 +408,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
     for (int j = 0; j < NT; j++) {
       if (2 * i + wm - 4 * j - wn < sym_thr) continue;      // above the diagonal of a symmetric tile: not produced
-      const int col = j0 + (4 * j + wn) * 8 + tq * 2;
+      const int col = j0 + (WN * j + wn) * 8 + tq * 2;
       double2* dst = reinterpret_cast<double2*>(Cg + (long long)row * p.ldc + col);
       double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
       if (beta != 0.0 && !init_from_c) {        // alpha == 0: C is only scaled
@@ -428,7 +452,7 @@ inline TgEncodeFn tg_encode_fn() {
 // rows x K operand with row/col layout flag, leading dimension ld, two batch levels (inner count/stride, outer
 // count/stride; strides in elements).  Returns false when the operand cannot be described (caller falls back).
 inline bool tg_make_map(CUtensorMap* map, const double* base, bool kmaj, int rows, int K, int ld, int inner,
-                        long long istride, int outer, long long ostride) {
+                        long long istride, int outer, long long ostride, int box_rows = TG_BM) {
   TgEncodeFn enc = tg_encode_fn();
   if (!enc) return false;
   if (((uintptr_t)base & 15) || (ld & 1)) return false;
@@ -438,23 +462,25 @@ inline bool tg_make_map(CUtensorMap* map, const double* base, bool kmaj, int row
   if (kmaj) {
     cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 8, ib, ob};
-    cuuint32_t box[4] = {(cuuint32_t)TG_BK, (cuuint32_t)TG_BM, 1, 1}, es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)TG_BK, (cuuint32_t)box_rows, 1, 1}, es[4] = {1, 1, 1, 1};
     r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     cuuint64_t dims[5] = {8, (cuuint64_t)K, (cuuint64_t)(rows / 8), (cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[4] = {(cuuint64_t)ld * 8, 64, ib, ob};
-    cuuint32_t box[5] = {8, (cuuint32_t)TG_BK, (cuuint32_t)(TG_BM / 8), 1, 1}, es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box[5] = {8, (cuuint32_t)TG_BK, (cuuint32_t)(box_rows / 8), 1, 1}, es[5] = {1, 1, 1, 1, 1};
     r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   return r == CUDA_SUCCESS;
 }
 
-template <bool A_KMAJ, bool B_KMAJ>
+template <bool A_KMAJ, bool B_KMAJ, int WN = 4>
 cudaError_t launch_gemm_tma_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TmaGemmParams& tp, int grid,
                                 cudaStream_t st) {
-  auto kern = gemm_tma_kernel<A_KMAJ, B_KMAJ>;
+  auto kern = gemm_tma_kernel<A_KMAJ, B_KMAJ, WN>;
+  constexpr size_t TG_SMEM_BYTES = TgCfg<WN>::SMEM_BYTES;
+  constexpr int TG_THREADS = TgCfg<WN>::THREADS;
   static PerDeviceOnce once;
   bool& attr_set = *once.slot();
   if (!attr_set) {
@@ -502,29 +528,39 @@ inline TgSchedTable& tg_sched_table() {
 // tile's panels while the MMA warps finish and store the current one (no per-tile launch / barrier-init / first-load
 // latency; batched small problems, where a tile is only 64-256 deep).  0: one CTA per work item, heavy tiles first -
 // the hardware scheduler balances and SMs free up for a high-priority panel chain as tiles retire.
+// `narrow`: 128 x 64 tiles, two CTAs per SM (TgCfg<2>); needs N % 64 == 0 and no lower_only.
 inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p, int batch_outer, cudaStream_t st,
-                                   int persistent_ctas = 0) {
-  if (p.M % TG_BM || p.N % TG_BN || p.K % TG_BK || p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorNotSupported;
+                                   int persistent_ctas = 0, bool narrow = false) {
+  const int BN = narrow ? 64 : TG_BN;
+  if (narrow && p.lower_only) return cudaErrorNotSupported;
+  if (p.M % TG_BM || p.N % BN || p.K % TG_BK || p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorNotSupported;
   if (((uintptr_t)p.C & 15) || (p.ldc & 1)) return cudaErrorNotSupported;
   CUtensorMap mA, mB;
   if (!tg_make_map(&mA, p.A, a_kmaj, p.M, p.K, p.lda, p.inner, p.iA, batch_outer, p.sA)) return cudaErrorNotSupported;
-  if (!tg_make_map(&mB, p.B, b_kmaj, p.N, p.K, p.ldb, p.inner, p.iB, batch_outer, p.sB)) return cudaErrorNotSupported;
+  if (!tg_make_map(&mB, p.B, b_kmaj, p.N, p.K, p.ldb, p.inner, p.iB, batch_outer, p.sB, BN)) return cudaErrorNotSupported;
   TmaGemmParams tp;
   tp.C = p.C; tp.ldc = p.ldc; tp.sC = p.sC; tp.iC = p.iC; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.inner = p.inner;
   tp.alpha = p.alpha; tp.beta = p.beta; tp.lower_only = p.lower_only; tp.kmode = p.kmode; tp.heavy_first = p.heavy_first;
-  const int tm = p.M / TG_BM, tn = p.N / TG_BN;
+  const int tm = p.M / TG_BM, tn = p.N / BN;
   const int tiles = p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   const long long total = (long long)tiles * batch_outer * p.inner;
   if (total > 0x7fffffffLL) return cudaErrorNotSupported;
   tp.tiles = tiles; tp.total = (int)total; tp.zero = 0;
   int grid = (int)total;
   tp.sched = nullptr;
+  if (narrow) persistent_ctas *= 2;                      // two CTAs per SM
   if (persistent_ctas > 0 && total > persistent_ctas) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
       tp.sched = tg_sched_table().slot(st);
       if (tp.sched) grid = persistent_ctas;
     }
+  }
+  if (narrow) {
+    if (a_kmaj && b_kmaj) return launch_gemm_tma_cfg<true, true, 2>(mA, mB, tp, grid, st);
+    if (a_kmaj && !b_kmaj) return launch_gemm_tma_cfg<true, false, 2>(mA, mB, tp, grid, st);
+    if (!a_kmaj && b_kmaj) return launch_gemm_tma_cfg<false, true, 2>(mA, mB, tp, grid, st);
+    return launch_gemm_tma_cfg<false, false, 2>(mA, mB, tp, grid, st);
   }
   if (a_kmaj && b_kmaj) return launch_gemm_tma_cfg<true, true>(mA, mB, tp, grid, st);
   if (a_kmaj && !b_kmaj) return launch_gemm_tma_cfg<true, false>(mA, mB, tp, grid, st);

@@ -10,9 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('persist', ['0', '2'])
-def test_gemm_all_modes(persist):
-    env = dict(os.environ, FFGP_PERSIST=persist)
+@pytest.mark.parametrize('persist,n64', [('0', '1'), ('2', '1'), ('0', '2'), ('2', '2'), ('2', '0')])
+def test_gemm_all_modes(persist, n64):
+    # FFGP_GEMM_N64=2 forces the 128 x 64-tile variant (two CTAs per SM) wherever it is eligible, 0 disables it
+    env = dict(os.environ, FFGP_PERSIST=persist, FFGP_GEMM_N64=n64)
     # the persistent grid is run three times: the stage-release race it once exposed hit ~1 tile in 500 (gemm_tma.cuh)
     for _ in range(3 if persist == '2' else 1):
         r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'check_gemm.py')], env=env, capture_output=True,

@@ -21,7 +21,9 @@ for akm, bkm, kmode in itertools.product((1, 0), (1, 0), range(5)):
     for lower_only, batch, (M, N, K), beta in (
             (0, 1, (256, 384, 256), 0.0), (0, 300, (128, 128, 128), 0.0), (0, 160, (256, 256, 256), 0.0),
             (1, 170, (384, 384, 384), 1.0), (0, 9, (512, 512, 512), -0.5), (0, 200, (256, 256, 256), 1.0),
-            (1, 170, (384, 384, 384), 0.0), (1, 400, (128, 128, 128), 1.0), (0, 1, (1024, 1024, 512), 0.5)):
+            (1, 170, (384, 384, 384), 0.0), (1, 400, (128, 128, 128), 1.0), (0, 1, (1024, 1024, 512), 0.5),
+            # 64-wide / 192-wide outputs: the 128 x 64-tile variant (two CTAs per SM), also forced by FFGP_GEMM_N64=2
+            (0, 320, (128, 64, 128), 0.0), (0, 200, (256, 192, 256), 1.0), (0, 310, (128, 128, 256), -0.5), (0, 150, (512, 64, 512), 0.0)):
         if kmode in (1, 4) and M > K: continue
         if kmode in (2, 3) and N > K: continue
         if kmode in (1, 2, 3, 4) and (M != K or N != K) and lower_only: continue

@@ -22,7 +22,7 @@ def run(akm, bkm, kmode, M, N, K, batch, lower=0, beta=0.0):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 10 * 1e3
 nb = 4 * 148
-print('persist', os.environ.get('FFGP_PERSIST', '1'))
+print('persist', os.environ.get('FFGP_PERSIST', '1'), 'n64', os.environ.get('FFGP_GEMM_N64', '1'))
 for name, akm, bkm, kmode in (('dense  A[i][p] B[j][p]', 1, 1, 0), ('dense  A[i][p] B[p][j]', 1, 0, 0), ('dense  A[p][i] B[p][j]', 0, 0, 0),
                               ('K_LE_COL (trsm  L21 = A21 M11^T)', 1, 1, 2), ('K_LE_ROW (T = M22 L21)', 1, 0, 1),
                               ('K_GE_COL (M21 = -T M11)', 1, 0, 3), ('K_GE_ROW (S = M^T M)', 0, 0, 4)):
