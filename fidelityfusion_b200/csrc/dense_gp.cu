@@ -10,6 +10,7 @@
 #include "dense_kernels.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_tma.cuh"
+#include "factor256.cuh"
 #include "xgrad_kernels.cuh"
 #include "acq_kernels.cuh"
 #include "train_kernels.cuh"
@@ -118,6 +119,17 @@ static int syrk_reserve() {
 static int persist_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FFGP_PERSIST"); v = e ? atoi(e) : 1; }
+  return v;
+}
+// FFGP_F256: 1 (default) batched problems factor and invert a 256 x 256 diagonal block with ONE launch of
+// factor256_kernel (csrc/factor256.cuh: one CTA per problem runs the two base blocks and the four 128-cube products
+// between them without leaving the SM); 2: the same without the structural-zero skipping; 3: also for single problems;
+// 0: two base kernels + four GEMM launches.  Measured (profiles/r02_factor256.txt): 592 x (N = 512) potrf + trtri
+// 3.53 -> 3.41 ms; a single problem does NOT gain - its four products spread over several SMs as 64-tiles and the chain
+// of a right-looking step at N = 8192 is 150 us either way (20.33 vs 20.24 ms per evaluation) - so it keeps the six launches.
+static int f256_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_F256"); v = e ? atoi(e) : 1; }
   return v;
 }
 static thread_local const char* g_trace_label = "gemm";
@@ -328,6 +340,13 @@ static cudaError_t factor_rec(const FactorCtx& c, int off, int n) {
           c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part, c.nblk, off / BASE_N_BATCHED, c.info, off);
     ++g_launches;
     trace_mark("base", off, 0, c.st);
+    return cudaGetLastError();
+  }
+  if (n == 2 * BASE_N && c.base_n == BASE_N && f256_mode() != 0 && (c.batch >= 8 || f256_mode() == 3)) {
+    factor256_kernel<<<c.batch, 256, F2_SMEM, c.st>>>(c.A + d0, c.L + d0, c.M + d0, c.ld, c.sb, c.logdet_part, c.nblk,
+                                                      off / BASE_N_BATCHED, c.info, off, f256_mode() == 2 ? 0 : 1);
+    ++g_launches;
+    trace_mark("f256", off, 0, c.st);
     return cudaGetLastError();
   }
   // split at a multiple of the base block: top half gets the larger power-of-two-ish share
@@ -632,6 +651,8 @@ static cudaError_t ensure_attrs() {
   bool& g_attr_done = *once.slot();
   if (g_attr_done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(factor256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N_BATCHED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;

@@ -242,36 +242,22 @@ __device__ __forceinline__ void solve8_row(double (&a)[8], const double (&l)[8][
 __device__ __forceinline__ void base_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void base_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// The factorisation proper, on a block that is already in shared memory: sm = T[BN][BN + 1] (lower part A, the inverse
+// part initialised to the identity) followed by the scratch area laid out below (base_smem_bytes).  All 256 threads of
+// the CTA call it; T is valid for every thread after the caller's next __syncthreads().  Returns the first failing
+// column (every thread tracks the same value) or -1.  Shared by potrf_trtri_base_kernel and factor256_kernel.
 template <int BN>
-__global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel(
-    const double* __restrict__ A, double* __restrict__ L, double* __restrict__ M, int ld, long long sbatch,
-    double* __restrict__ logdet_part, int logdet_stride, int blk, int* __restrict__ info, int row_offset) {
+__device__ __forceinline__ int base_factor_smem(double* __restrict__ sm, const int tid) {
   constexpr int BASE_N = BN, BASE_LD = BN + 1, QV = BN / 32;       // QV: 32-wide groups of virtual columns per lane
   static_assert(BN == 64 || BN == 128, "base block is 64 or 128");
-  extern __shared__ __align__(16) double sm[];
   double* T = sm;                                   // [BN][BN + 1]
   double* F = sm + BASE_N * BASE_LD;                // [2][BASE_F] published diagonal factors (double-buffered)
   double* Dn = F + 2 * BASE_F;                      // [36] updated next diagonal block (warp 0 scratch)
-  double* red = Dn + 64;
   // sink for masked stores / source of masked loads: one slot PER THREAD, so that the branch-free masking below is not a
   // (benign) shared-memory race between threads - compute-sanitizer racecheck stays clean (profiles/r02_sanitizer.txt)
-  const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   const int DUMMY = BASE_N * BASE_LD + 2 * BASE_F + 136 + tid;
-  A += b * sbatch; L += b * sbatch; M += b * sbatch;
 #define TT(i, k) T[(i) * BASE_LD + (k)]
-  // block load: every element is an independent 8-byte cp.async (all in flight at once; a plain load loop
-  // serialises 64 global-memory latencies per thread on the single resident CTA)
-  for (int e = tid; e < BASE_N * BASE_N; e += 256) {
-    const int i = e / BASE_N, k = e % BASE_N;
-    if (k <= i) {
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&TT(i, k));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(A + (long long)i * ld + k));
-      TT(k, i + 1) = (i == k) ? 1.0 : 0.0;
-    }
-  }
-  asm volatile("cp.async.commit_group;\n" ::);
-  asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
   int fail_col = -1;
   double l[8][8], inv[8];
   {  // factor of the first diagonal block: every thread redundantly, thread 0 stores it
@@ -454,15 +440,20 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
           cacc[a][q] = T[idx[a][q]];
         }
       }
+      // the 32 panel entries of the quad's rows are requested up front (broadcast loads, all in flight together): with
+      // them inside the kk loop every rank-1 step started with a shared-memory round trip and a quad took ~1150 clk
+      // for 128 FMAs per lane (profiles/r02_base_kernel_timeline_v3.txt)
+      double av[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) av[a][kk] = -TT(i0 + a, j0 + kk);
 #pragma unroll
       for (int kk = 0; kk < 8; kk++) {
-        double av[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) av[a] = -TT(i0 + a, j0 + kk);
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int q = 0; q < QV; q++) cacc[a][q] = fma(av[a], bv[kk][q], cacc[a][q]);
+          for (int q = 0; q < QV; q++) cacc[a][q] = fma(av[a][kk], bv[kk][q], cacc[a][q]);
       }
 #pragma unroll
       for (int q = 0; q < QV; q++)
@@ -471,6 +462,35 @@ __global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel
     }
     BASE_STAMP(p, 3);
   }
+  return fail_col;
+#undef TT
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, BN == 64 ? 2 : 1) potrf_trtri_base_kernel(
+    const double* __restrict__ A, double* __restrict__ L, double* __restrict__ M, int ld, long long sbatch,
+    double* __restrict__ logdet_part, int logdet_stride, int blk, int* __restrict__ info, int row_offset) {
+  constexpr int BASE_N = BN, BASE_LD = BN + 1;
+  extern __shared__ __align__(16) double sm[];
+  double* T = sm;
+  double* red = sm + BASE_N * BASE_LD + 2 * BASE_F + 64;
+  const int tid = threadIdx.x, b = blockIdx.x;
+  A += b * sbatch; L += b * sbatch; M += b * sbatch;
+#define TT(i, k) T[(i) * BASE_LD + (k)]
+  // block load: every element is an independent 8-byte cp.async (all in flight at once; a plain load loop
+  // serialises 64 global-memory latencies per thread on the single resident CTA)
+  for (int e = tid; e < BASE_N * BASE_N; e += 256) {
+    const int i = e / BASE_N, k = e % BASE_N;
+    if (k <= i) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&TT(i, k));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(A + (long long)i * ld + k));
+      TT(k, i + 1) = (i == k) ? 1.0 : 0.0;
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  const int fail_col = base_factor_smem<BN>(sm, tid);
   __syncthreads();
   for (int e = tid; e < BASE_N * BASE_N; e += 256) {
     const int i = e / BASE_N, k = e % BASE_N;

@@ -1,22 +1,25 @@
 // Internal timeline of potrf_trtri_base_kernel (clock64 stamps per warp / panel / phase).
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DFFGP_BASE_TRACE -o tools/base_trace tools/base_trace.cu
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DFFGP_BASE_TRACE [-DTRACE_BN=64] -o tools/base_trace tools/base_trace.cu
 #include <cstdio>
 #include <vector>
 #include <cmath>
 #include "../fidelityfusion_b200/csrc/dense_kernels.cuh"
 using namespace ffgp;
+#ifndef TRACE_BN
+#define TRACE_BN 128
+#endif
 int main() {
-  const int n = 128;
+  const int n = TRACE_BN;
   std::vector<double> h(n * n);
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) h[i * n + j] = exp(-0.05 * (i - j) * (i - j)) + (i == j ? 0.5 : 0.0);
   double *A, *L, *M, *ld; int* info;
   cudaMalloc(&A, n * n * 8); cudaMalloc(&L, n * n * 8); cudaMalloc(&M, n * n * 8); cudaMalloc(&ld, 64); cudaMalloc(&info, 4);
   cudaMemcpy(A, h.data(), n * n * 8, cudaMemcpyHostToDevice); cudaMemset(info, 0, 4);
-  cudaFuncSetAttribute(potrf_trtri_base_kernel<BASE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_SMEM);
-  for (int it = 0; it < 3; it++) potrf_trtri_base_kernel<BASE_N><<<1, 256, BASE_SMEM>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
+  cudaFuncSetAttribute(potrf_trtri_base_kernel<TRACE_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base_smem_bytes(TRACE_BN));
+  for (int it = 0; it < 3; it++) potrf_trtri_base_kernel<TRACE_BN><<<1, 256, base_smem_bytes(TRACE_BN)>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  for (int it = 0; it < 10; it++) potrf_trtri_base_kernel<BASE_N><<<1, 256, BASE_SMEM>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
+  for (int it = 0; it < 10; it++) potrf_trtri_base_kernel<TRACE_BN><<<1, 256, base_smem_bytes(TRACE_BN)>>>(A, L, M, n, 0, ld, 1, 0, info, 0);
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("base kernel: %.2f us per launch (%s)\n", ms * 100, cudaGetErrorString(cudaGetLastError()));
@@ -24,7 +27,7 @@ int main() {
   cudaMemcpyFromSymbol(tr.data(), g_base_trace, tr.size() * 8);
   long long t0 = tr[0];
   printf("panel: t(top)  | w0: solve  diag-upd  chol8+publish | w1: solve+wait  hoist  update | panel total\n");
-  for (int p = 0; p < 15; p++) {
+  for (int p = 0; p < TRACE_BN / 8 - 1; p++) {
     auto w0 = [&](int s) { return tr[(0 * 16 + p) * 4 + s]; };
     auto w1 = [&](int s) { return tr[(1 * 16 + p) * 4 + s]; };
     long long nxt = tr[(0 * 16 + p + 1) * 4 + 0];
