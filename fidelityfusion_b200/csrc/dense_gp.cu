@@ -226,7 +226,19 @@ struct DenseWs {
   size_t bytes;
 };
 
-static const size_t WS_TARGET_BYTES = (size_t)6 << 30;   // per-chunk working set bound for big batches
+// Per-chunk working set bound for big batches (FFGP_WS_GB, default 32 GiB of the B200's 180 GB).  Every launch of a chunk
+// streams the whole chunk through HBM whatever its size, so a smaller chunk buys no locality; it only multiplies the ~35
+// dependent launches of an evaluation (each with ~11 us of ramp-up and drain) by the number of chunks.  BASELINE config 5
+// (4096 x N = 512): 5 chunks of <= 888 problems under the round-1 bound of 6 GiB, ONE chunk of 26 GiB now.
+static size_t ws_target_bytes() {
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("FFGP_WS_GB");
+    const long long gb = e ? atoll(e) : 32;
+    v = (size_t)(gb < 1 ? 1 : gb) << 30;
+  }
+  return v;
+}
 
 static DenseWs layout_ws(int n, int d, int D, int ns, int batch, char* base) {
   DenseWs w;
@@ -251,7 +263,7 @@ static DenseWs layout_ws(int n, int d, int D, int ns, int batch, char* base) {
     return s;
   };
   const size_t item = per_item();
-  long long chunk = (long long)(WS_TARGET_BYTES / item);
+  long long chunk = (long long)(ws_target_bytes() / item);
   if (chunk < 1) chunk = 1;
   {  // balanced chunks: 1024 problems with room for 1016 must not become 1016 + 8 (the tail chunk pays every launch
      // latency of a full one, profiles/r01_metrics_c5_v1.txt)
@@ -772,6 +784,9 @@ int ffgp_trace_dump(void) {
   g_ntrace = 0;
   return n;
 }
+#ifdef FFGP_TG_TRACE
+int ffgp_debug_tg_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tg_trace, sizeof(long long) * 32 * 6); }
+#endif
 unsigned long long ffgp_launch_count(void) { return g_launches; }
 const char* ffgp_last_error_string(void) { return g_err; }
 

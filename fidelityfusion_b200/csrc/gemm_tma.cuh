@@ -151,6 +151,15 @@ __device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int w) {
   return r;
 }
 
+#ifdef FFGP_TG_TRACE
+// Per-tile timeline of consumer warp 0 of CTA 0 (tools/tg_trace.py): clock64 at tile start | accumulators initialised |
+// first stage arrived + first fragments requested | main loop done | epilogue done | next tile id known.
+__device__ long long g_tg_trace[32 * 6];
+#define TG_STAMP(n, s) do { if (blockIdx.x == 0 && warp == 0 && lane == 0 && (n) < 32) g_tg_trace[(n) * 6 + (s)] = clock64(); } while (0)
+#else
+#define TG_STAMP(n, s) do { } while (0)
+#endif
+
 // A_KMAJ: A(i,p) = A[i*lda + p]  else  A(i,p) = A[p*lda + i];   B_KMAJ: B(p,j) = B[j*ldb + p]  else  B[p*ldb + j]
 template <bool A_KMAJ, bool B_KMAJ, int WN = 4>
 __global__ void __launch_bounds__(TgCfg<WN>::THREADS, TgCfg<WN>::CTAS_PER_SM)
@@ -257,6 +266,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   int it0 = 0;                                     // k-steps consumed before this tile (the stage ring runs on across tiles)
   int w = blockIdx.x;
   for (int n = 0;; n++) {
+  TG_STAMP(n, 0);
   const TgTile tl = tg_decode<TG_BN>(p, w);
   const int ti = tl.ti, tj = tl.tj, i0 = ti * TG_BM, j0 = tj * TG_BN, k_hi = tl.k_hi;
   const int KT = (tl.k_hi - tl.k_lo) / TG_BK;
@@ -296,10 +306,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       for (int j = 0; j < NT; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   }
 
+  TG_STAMP(n, 1);
   if (KT > 0) {
     tg_mbar_wait(bar_base + 8 * (it0 % TG_STAGES), (it0 / TG_STAGES) & 1);
     load_frags(0, smem_base + (it0 % TG_STAGES) * TG_STAGE_BYTES, 0);
   }
+  TG_STAMP(n, 2);
   // One k-step (16 deep = 4 k4 steps) with the compile-time set of live fragments `Lv`: straight-line DMMAs, no
   // per-instruction predicates (a first version predicated every DMMA: the compiler guards each with WARPSYNC + a
   // chain of ISETPs and the "skipped" work cost more than doing it, profiles/r01_c5_trisk_v1.txt).
@@ -401,6 +413,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
   }
 
+  TG_STAMP(n, 3);
   // ---- epilogue: C fragment (row g, cols 2 tq, 2 tq + 1) -> 16-byte stores ----------------------
 #pragma unroll
   for (int i = 0; i < MT; i++) {
@@ -420,10 +433,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
   }
   it0 += KT;
+  TG_STAMP(n, 4);
   if (!p.sched) break;
   // next work item of this CTA: its id is valid once the first stage of the tile (or the end marker) has been posted
   tg_mbar_wait(bar_base + 8 * (it0 % TG_STAGES), (it0 / TG_STAGES) & 1);
   w = tile_ring[(n + 1) % TG_TILE_RING];
+  TG_STAMP(n, 5);
   if (w < 0) break;
   }   // tile loop
 }
