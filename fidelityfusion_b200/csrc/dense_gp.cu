@@ -785,7 +785,7 @@ int ffgp_trace_dump(void) {
   return n;
 }
 #ifdef FFGP_TG_TRACE
-int ffgp_debug_tg_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tg_trace, sizeof(long long) * 32 * 6); }
+int ffgp_debug_tg_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tg_trace, sizeof(long long) * 2 * 32 * 6); }
 #endif
 unsigned long long ffgp_launch_count(void) { return g_launches; }
 const char* ffgp_last_error_string(void) { return g_err; }

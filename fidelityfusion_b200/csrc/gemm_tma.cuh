@@ -37,7 +37,7 @@ constexpr int TG_REGS_PRODUCER = 40, TG_REGS_CONSUMER = 232;
 constexpr int TG_PANEL_BYTES = TG_BM * TG_BK * 8;                       // 16 KB per operand per stage
 constexpr int TG_STAGE_BYTES = 2 * TG_PANEL_BYTES;
 constexpr int TG_TILE_RING = 8;                                         // > TG_STAGES: the producer is at most TG_STAGES tiles ahead
-constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/ + 4 * TG_TILE_RING;
+constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/ + 4 * TG_TILE_RING + 16 /*stagger flag*/;
 
 // Tile shape by the number of warp COLUMNS WN (warp tile 64 x 32 either way, same per-warp code and register budget):
 //   WN = 4: 128 x 128 tile, 8 MMA warps + producer warpgroup = 384 threads, 6 x 32 KB stages, ONE CTA per SM
@@ -57,7 +57,7 @@ struct TgCfg {
   static constexpr int STAGE_BYTES = TG_PANEL_BYTES + B_PANEL_BYTES;
   static constexpr int REGS_PRODUCER = WN == 4 ? TG_REGS_PRODUCER : 24;
   static constexpr int CTAS_PER_SM = WN == 4 ? 1 : 2;
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 128 + 4 * TG_TILE_RING;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 128 + 4 * TG_TILE_RING + 16;
 };
 
 struct TmaGemmParams {
@@ -69,6 +69,7 @@ struct TmaGemmParams {
   int lower_only, kmode, heavy_first;
   int zero;                  // always 0 (a run-time value the compiler cannot fold, see the stage release)
   int tiles, total;          // tiles per problem, work items of the launch (tiles x problems); grid.x <= total
+  int stagger;               // persistent grid only: k-steps by which the second warp row starts behind the first (0: off)
   unsigned int* sched;       // NULL: one work item per CTA (grid.x == total).  Else {next, done} counters, both zero at
                              // launch and reset by the last CTA: CTAs fetch further work items as they finish
 };
@@ -154,8 +155,8 @@ __device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int w) {
 #ifdef FFGP_TG_TRACE
 // Per-tile timeline of consumer warp 0 of CTA 0 (tools/tg_trace.py): clock64 at tile start | accumulators initialised |
 // first stage arrived + first fragments requested | main loop done | epilogue done | next tile id known.
-__device__ long long g_tg_trace[32 * 6];
-#define TG_STAMP(n, s) do { if (blockIdx.x == 0 && warp == 0 && lane == 0 && (n) < 32) g_tg_trace[(n) * 6 + (s)] = clock64(); } while (0)
+__device__ long long g_tg_trace[2 * 32 * 6];           // [warp 0 | warp 4 (same SM sub-partition)][tile][stamp]
+#define TG_STAMP(n, s) do { if (blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && (n) < 32) g_tg_trace[((warp >> 2) * 32 + (n)) * 6 + (s)] = clock64(); } while (0)
 #else
 #define TG_STAMP(n, s) do { } while (0)
 #endif
@@ -173,7 +174,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   volatile int* tile_ring = reinterpret_cast<volatile int*>(tg_smem_raw + (smem_base - tg_smem_u32(tg_smem_raw)) +
                                                             TG_STAGES * TG_STAGE_BYTES + 128);
 
+  volatile int* stagger_go = tile_ring + TG_TILE_RING;
   if (tid == 0) {
+    *stagger_go = 0;
     for (int s = 0; s < TG_STAGES; s++) {
       tg_mbar_init(bar_base + 8 * s, 1);                           // full: one arrive.expect_tx by the producer
       tg_mbar_init(bar_base + 64 + 8 * s, TG_CONSUMER_WARPS);      // empty: one arrive per consumer warp
@@ -265,6 +268,21 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   double acc[MT][NT][2];
   int it0 = 0;                                     // k-steps consumed before this tile (the stage ring runs on across tiles)
   int w = blockIdx.x;
+  // Stagger experiment (FFGP_STAGGER = k-steps, default 0 = off; persistent grid only).  Warps w and w + 4 share an SM
+  // sub-partition; started together, both reach every tile's epilogue + accumulator init (~4.4k clk per tile) at the same
+  // moment and the DMMA pipe idles.  Starting the second warp row `stagger` k-steps late keeps the rows out of phase for
+  // all of the CTA's tiles (measured: the 17k-clk offset persists) - but a tile takes 38.6k clk either way
+  // (profiles/r02_c5_experiments.txt): alone on its sub-partition a warp of this main loop issues a DMMA per 22.5 clk
+  // (17.4 when two share the pipe), and the other row's 32 STG.128 per thread sit in the same load/store path as this
+  // row's fragment loads, so the hand-over is not hidden.  Kept as a knob; the offset must stay below TG_STAGES.
+  const bool staggered = p.sched != nullptr && p.stagger > 0;
+  if (staggered && wm == 1) {
+#pragma unroll 1
+    for (uint32_t spin = 0; *stagger_go == 0; ++spin) {
+      __nanosleep(64);
+      if (spin > (1u << 24)) __trap();                 // a protocol bug must surface as a trap, never as a hung GPU
+    }
+  }
   for (int n = 0;; n++) {
   TG_STAMP(n, 0);
   const TgTile tl = tg_decode<TG_BN>(p, w);
@@ -359,6 +377,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
   };
   for (int kt = 0; kt < KT; kt++) {
+#ifdef FFGP_TG_TRACE
+    if (n == 0 && kt < 8) TG_STAMP(24 + kt, 0);          // first tile: start of every k-step (rows 24.. of the trace)
+#endif
+    if (staggered && n == 0 && warp == 0 && lane == 0 && kt == min(p.stagger, KT - 1)) *stagger_go = 1;
     // variant of this k-step (warp-uniform): 0 dense | 1..7 i >= v | 8..14 i < v-7 | 15..17 j >= v-14 | 18..20 j < v-17 |
     // 21..28 symmetric diagonal tile, by warp role.  Ranges are the union over the four k4 steps of the k-step.
     int variant = 0;
@@ -413,6 +435,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
   }
 
+  if (staggered && n == 0 && KT == 0 && warp == 0 && lane == 0) *stagger_go = 1;
   TG_STAMP(n, 3);
   // ---- epilogue: C fragment (row g, cols 2 tq, 2 tq + 1) -> 16-byte stores ----------------------
 #pragma unroll
@@ -561,6 +584,11 @@ inline cudaError_t launch_gemm_tma(bool a_kmaj, bool b_kmaj, const GemmParams& p
   const long long total = (long long)tiles * batch_outer * p.inner;
   if (total > 0x7fffffffLL) return cudaErrorNotSupported;
   tp.tiles = tiles; tp.total = (int)total; tp.zero = 0;
+  {
+    static int stg = -1;                                 // FFGP_STAGGER: k-steps of offset between the two warp rows (0 = off)
+    if (stg < 0) { const char* e = getenv("FFGP_STAGGER"); stg = e ? atoi(e) : 0; if (stg < 0 || stg >= TG_STAGES) stg = 0; }
+    tp.stagger = narrow ? 0 : stg;
+  }
   int grid = (int)total;
   tp.sched = nullptr;
   if (narrow) persistent_ctas *= 2;                      // two CTAs per SM

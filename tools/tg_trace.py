@@ -19,14 +19,17 @@ def run(name, akm, bkm, kmode, M, N, K, batch, lower=0, beta=0.0):
                              C.data_ptr(), N, M * N, M, N, K, 1.0, beta, lower, kmode, batch, st)
         assert rc == 0
     torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (32 * 6))()
+    buf = (ctypes.c_longlong * (2 * 32 * 6))()
     assert L.ffgp_debug_tg_trace(buf) == 0
-    t = [[buf[n * 6 + s] for s in range(6)] for n in range(32)]
-    print(f'{name}: per tile (clk): init | first stage wait | main loop | epilogue | next-tile wait | total')
-    for n in range(1, 5):
-        r = t[n]
-        if r[5] <= r[0]: break
-        print(f'   tile {n}: {r[1]-r[0]:6d} {r[2]-r[1]:6d} {r[3]-r[2]:7d} {r[4]-r[3]:6d} {r[5]-r[4]:6d} | {t[n+1][0]-r[0] if t[n+1][0] > r[0] else r[5]-r[0]:7d}')
+    print(f'{name}: per tile (clk): init | first stage wait | main loop | epilogue | next-tile wait | total      (warp 0, then warp 4 with its main-loop start relative to warp 0)')
+    t0 = [[buf[n * 6 + s] for s in range(6)] for n in range(32)]
+    print('   first tile, warp 0, clk per k-step:', [t0[24 + k + 1][0] - t0[24 + k][0] for k in range(7)])
+    for wv in (0, 1):
+        t = [[buf[(wv * 32 + n) * 6 + s] for s in range(6)] for n in range(32)]
+        for n in range(1, 4):
+            r = t[n]
+            if r[5] <= r[0]: break
+            print(f'   w{4 * wv} tile {n}: {r[1]-r[0]:6d} {r[2]-r[1]:6d} {r[3]-r[2]:7d} {r[4]-r[3]:6d} {r[5]-r[4]:6d} | {t[n+1][0]-r[0] if t[n+1][0] > r[0] else r[5]-r[0]:7d}   offset {r[2]-t0[n][2]:7d}')
 nb = 8 * 148
 run('dense 128-cube  A[i][p] B[j][p]', 1, 1, 0, 128, 128, 128, nb)
 run('K_LE_COL 128 (L21 = A21 M11^T)', 1, 1, 2, 128, 128, 128, nb)
