@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libffgp.so')
+# FFGP_LIB_PATH: A/B runs of two builds of the SAME C ABI on one box (tools/); production loads the in-tree library
+LIB_PATH = os.environ.get('FFGP_LIB_PATH') or os.path.join(_HERE, 'libffgp.so')
 _lib = None
 
 c_dp = ctypes.c_void_p

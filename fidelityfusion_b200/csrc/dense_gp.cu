@@ -709,6 +709,7 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   kp.symmetric = 1; kp.lower_only = 1; kp.clamp = a.clamp;
   kernel_matrix_kernel<<<dim3(w.np / 64, w.np / 64, nb), 256, 0, st>>>(kp);
   FFGP_LAUNCHED();
+  trace_mark("kernel_matrix", 0, 0, st);
   FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};
   c.base_n = (nb >= 8 && batched_base64()) ? BASE_N_BATCHED : BASE_N;
   // one log-det slot per 64 rows; with 128-blocks only every other slot is written
@@ -734,18 +735,22 @@ static int solve_rhs(const DenseArgs& a, const DenseWs& w, int b0, int nb, cudaS
     trmv_lower_kernel<8><<<dim3(w.np / 8, nb), 256, 0, st>>>(w.M, w.np, sM, y, a.n, a.D, (long long)a.n * a.D, w.Gm, sG,
                                                              w.rowsq, w.np);
     FFGP_LAUNCHED();
+    trace_mark("trmv_lower", 0, 0, st);
     colsum_weighted_kernel<8><<<dim3(w.np / 32, nb), 256, 0, st>>>(w.M, w.np, sM, w.np, w.Gm, a.D, sG, a.D, w.alpha, a.D,
                                                                    sG, w.np, 1, 0);
     FFGP_LAUNCHED();
+    trace_mark("colsum_weighted", 0, 0, st);
   } else {
     const long long sG = (long long)w.np * w.Dp;
     dim3 blk(32, 8), grd((w.Dp + 31) / 32, (w.np + 7) / 8, nb);
     pad_copy_kernel<<<grd, blk, 0, st>>>(y, a.n, a.D, a.D, (long long)a.n * a.D, w.Ypad, w.np, w.Dp, w.Dp, sG);
     FFGP_LAUNCHED();
+    trace_mark("pad_copy", 0, 0, st);
     FFGP_CUDA(gemm(true, false, w.M, w.np, sM, w.Ypad, w.Dp, sG, w.Gm, w.Dp, sG, w.np, w.Dp, w.np, 1.0, 0.0, 0, K_LE_ROW,
                    nb, st));
     rowsq_kernel<<<dim3(w.np / 8, nb), 256, 0, st>>>(w.Gm, w.Dp, sG, w.Dp, w.rowsq, w.np);
     FFGP_LAUNCHED();
+    trace_mark("rowsq", 0, 0, st);
     FFGP_CUDA(gemm(false, false, w.M, w.np, sM, w.Gm, w.Dp, sG, w.alpha, w.Dp, sG, w.np, w.Dp, w.np, 1.0, 0.0, 0,
                    K_GE_ROW, nb, st));
   }
@@ -759,6 +764,7 @@ static int copy_alpha_out(const DenseArgs& a, const DenseWs& w, int b0, int nb, 
   pad_copy_kernel<<<grd, blk, 0, st>>>(w.alpha, w.np, Dw, Dw, (long long)w.np * Dw,
                                        out_alpha + (long long)b0 * a.n * a.D, a.n, a.D, a.D, (long long)a.n * a.D);
   FFGP_LAUNCHED();
+  trace_mark("pad_copy", 0, 0, st);
   return 0;
 }
 
@@ -785,6 +791,7 @@ int ffgp_trace_dump(void) {
   return n;
 }
 #ifdef FFGP_TG_TRACE
+int ffgp_debug_tg_cta(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tg_cta, sizeof(long long) * 4096 * 4); }
 int ffgp_debug_tg_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tg_trace, sizeof(long long) * 2 * 32 * 6); }
 #endif
 unsigned long long ffgp_launch_count(void) { return g_launches; }
@@ -822,6 +829,7 @@ int ffgp_kernel_matrix_f64(const double* x1, const double* x2, const double* inv
   kp.symmetric = 0; kp.lower_only = 0; kp.clamp = clamp; kp.bounded = 1;
   kernel_matrix_kernel<<<dim3(kp.np2 / 64, kp.np1 / 64, batch), 256, 0, st>>>(kp);
   FFGP_LAUNCHED();
+  trace_mark("kernel_matrix", 0, 0, st);
   return 0;
 }
 
@@ -876,16 +884,19 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
       symv_lower_kernel<<<dim3(nb, D), 256, (size_t)9 * w.np * sizeof(double), st>>>(
           w.A, w.np, sM, n, w.np, y + (long long)b0 * n * D, D, (long long)n * D, w.alpha, sG, w.rowsq);
       FFGP_LAUNCHED();
+      trace_mark("symv_lower", 0, 0, st);
       if (D > 1) {
         rowdot_kernel<<<dim3((w.np + 255) / 256, nb), 256, 0, st>>>(y + (long long)b0 * n * D, (long long)n * D, w.alpha, sG, n,
                                                                      w.np, D, w.rowsq);
         FFGP_LAUNCHED();
+        trace_mark("rowdot", 0, 0, st);
       }
     }
     if (want_nll) {
       nll_reduce_kernel<<<nb, 256, 0, st>>>(w.rowsq, w.np, w.logdet_part, w.nblk, D, out_nll + b0,
                                             out_logdet ? out_logdet + b0 : nullptr);
       FFGP_LAUNCHED();
+      trace_mark("nll_reduce", 0, 0, st);
     }
     if (!reuse_factor && (rc = copy_alpha_out(a, w, b0, nb, out_alpha, st)) != 0) return rc;
     if (want_grad) {
@@ -915,10 +926,12 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
       if (gp.G_out) grad_contract_kernel<true><<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
       else grad_contract_kernel<false><<<dim3(w.ngtile, nb), 256, grad_smem_bytes(gp.d), st>>>(gp);
       FFGP_LAUNCHED();
+      trace_mark("grad_contract", 0, 0, st);
       if (amp) {
         grad_finish_kernel<<<dim3(d + 1, nb), 256, 0, st>>>(w.partial, w.ngtile, d, gp.w, gp.sw, gp.amp, gp.samp,
                                                             g_inv_ls + (long long)b0 * d, g_amp + b0);
         FFGP_LAUNCHED();
+        trace_mark("grad_finish", 0, 0, st);
       }
     }
     if (!want_pred) return 0;
@@ -938,6 +951,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
     }
     kernel_matrix_kernel<<<dim3(w.nsp / 64, w.np / 64, nb), 256, 0, st>>>(kp);
     FFGP_LAUNCHED();
+    trace_mark("kernel_matrix", 0, 0, st);
     // mean = Kx^T alpha
     if (!w.gemm_rhs) {
       colsum_weighted_kernel<8><<<dim3(w.nsp / 32, nb), 256, 0, st>>>(w.Kx, w.nsp, sKx, w.np, w.alpha, D,
@@ -945,6 +959,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
                                                                       out_mean + (long long)b0 * ns * D, D,
                                                                       (long long)ns * D, ns, 0, 0);
       FFGP_LAUNCHED();
+      trace_mark("colsum_weighted", 0, 0, st);
     } else {
       const long long sG = (long long)w.np * w.Dp, sMp = (long long)w.nsp * w.Dp;
       FFGP_CUDA(gemm(false, false, w.Kx, w.nsp, sKx, w.alpha, w.Dp, sG, w.meanp, w.Dp, sMp, w.nsp, w.Dp, w.np, 1.0, 0.0, 0,
@@ -953,6 +968,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
       pad_copy_kernel<<<grd, blk, 0, st>>>(w.meanp, w.nsp, w.Dp, w.Dp, sMp, out_mean + (long long)b0 * ns * D, ns, D, D,
                                            (long long)ns * D);
       FFGP_LAUNCHED();
+      trace_mark("pad_copy", 0, 0, st);
     }
     if (!out_cov) return 0;
     // V = M Kx
@@ -972,6 +988,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
       kq.offset = cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr; kq.soff = params_batched ? 1 : 0;
       kernel_matrix_kernel<<<dim3(w.nsp / 64, w.nsp / 64, nb), 256, 0, st>>>(kq);
       FFGP_LAUNCHED();
+      trace_mark("kernel_matrix", 0, 0, st);
       // cov = Kxx - V^T V
       FFGP_CUDA(gemm(false, false, w.V, w.nsp, sKx, w.V, w.nsp, sKx, w.Kxx, w.nsp, sKxx, w.nsp, w.nsp, w.np, -1.0, 1.0, 0,
                      K_FULL, nb, st));
@@ -979,15 +996,18 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
       unpad_copy_kernel<<<grd, blk, 0, st>>>(w.Kxx, w.nsp, sKxx, out_cov + (long long)b0 * ns * ns, ns, ns,
                                              (long long)ns * ns, 0);
       FFGP_LAUNCHED();
+      trace_mark("unpad_copy", 0, 0, st);
     } else {
       colsum_weighted_kernel<1><<<dim3(w.nsp / 32, nb), 256, 0, st>>>(w.V, w.nsp, sKx, w.np, nullptr, 0, 0, 1, w.colsq, 1,
                                                                       w.nsp, w.nsp, 0, 1);
       FFGP_LAUNCHED();
+      trace_mark("colsum_weighted", 0, 0, st);
       var_diag_kernel<<<dim3((ns + 127) / 128, nb), 128, 0, st>>>(w.colsq, amp + (params_batched ? b0 : 0),
                                                                   params_batched ? 1 : 0,
                                                                   cov_offset ? cov_offset + (params_batched ? b0 : 0) : nullptr,
                                                                   params_batched ? 1 : 0, out_cov + (long long)b0 * ns, ns, w.nsp);
       FFGP_LAUNCHED();
+      trace_mark("var_diag", 0, 0, st);
     }
     return 0;
   };

@@ -157,8 +157,11 @@ __device__ __forceinline__ TgTile tg_decode(const TmaGemmParams& p, int w) {
 // first stage arrived + first fragments requested | main loop done | epilogue done | next tile id known.
 __device__ long long g_tg_trace[2 * 32 * 6];           // [warp 0 | warp 4 (same SM sub-partition)][tile][stamp]
 #define TG_STAMP(n, s) do { if (blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && (n) < 32) g_tg_trace[((warp >> 2) * 32 + (n)) * 6 + (s)] = clock64(); } while (0)
+__device__ long long g_tg_cta[4096 * 4];                // non-persistent launches: per CTA {tile start, main loop start, main loop end, end}
+#define TG_CTA(s) do { if (!p.sched && blockIdx.x < 4096 && warp == 0 && lane == 0) g_tg_cta[blockIdx.x * 4 + (s)] = clock64(); } while (0)
 #else
 #define TG_STAMP(n, s) do { } while (0)
+#define TG_CTA(s) do { } while (0)
 #endif
 
 // A_KMAJ: A(i,p) = A[i*lda + p]  else  A(i,p) = A[p*lda + i];   B_KMAJ: B(p,j) = B[j*ldb + p]  else  B[p*ldb + j]
@@ -285,6 +288,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
   for (int n = 0;; n++) {
   TG_STAMP(n, 0);
+  TG_CTA(0);
   const TgTile tl = tg_decode<TG_BN>(p, w);
   const int ti = tl.ti, tj = tl.tj, i0 = ti * TG_BM, j0 = tj * TG_BN, k_hi = tl.k_hi;
   const int KT = (tl.k_hi - tl.k_lo) / TG_BK;
@@ -330,29 +334,40 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     load_frags(0, smem_base + (it0 % TG_STAGES) * TG_STAGE_BYTES, 0);
   }
   TG_STAMP(n, 2);
+  TG_CTA(1);
   // One k-step (16 deep = 4 k4 steps) with the compile-time set of live fragments `Lv`: straight-line DMMAs, no
   // per-instruction predicates (a first version predicated every DMMA: the compiler guards each with WARPSYNC + a
   // chain of ISETPs and the "skipped" work cost more than doing it, profiles/r01_c5_trisk_v1.txt).
+  // The four k4 steps of a k-step run as a ROLLED loop of two double-steps (fragment buffers 0 / 1 are compile-time
+  // inside an iteration).  Fully unrolled, a body was ~5 KB of SASS and the kernel 150 KB: the eight role bodies of a
+  // symmetric diagonal tile (one per warp) or the eight bodies a triangular K block walks through (one per k-step,
+  // each executed once per tile) exceed the 32 KB L1.5 instruction cache - `ncu --set full` of the batched
+  // S = M^T M launch: 20 % of the warp samples stalled on `no_instructions`, a symmetric 128-deep block took 28k clk
+  // for 17.4k clk of DMMA issue (profiles/r02_lauum_icache.txt).  Halving every body brings both working sets under it.
   auto kt_body = [&](auto lv, int kt) {
     using Lv = decltype(lv);
     const int s = (it0 + kt) % TG_STAGES;
     const uint32_t stage_base = smem_base + s * TG_STAGE_BYTES;
+    const bool has_next = kt + 1 < KT;
     uint32_t rel = 0;
-#pragma unroll
-    for (int kk = 0; kk < TG_BK / 4; kk++) {
-      const int cur = kk & 1, nxt = cur ^ 1;
-      if (kk < TG_BK / 4 - 1) {
-        load_frags(nxt, stage_base, kk + 1);
-      } else if (kt + 1 < KT) {
-        const int s2 = (it0 + kt + 1) % TG_STAGES;
-        tg_mbar_wait(bar_base + 8 * s2, ((it0 + kt + 1) / TG_STAGES) & 1);
-        load_frags(nxt, smem_base + s2 * TG_STAGE_BYTES, 0);
-      }
+    auto mma = [&](const int buf) {
 #pragma unroll
       for (int i = 0; i < MT; i++)
 #pragma unroll
         for (int j = 0; j < NT; j++)
-          if (Lv::live(i, j)) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+          if (Lv::live(i, j)) dmma884(acc[i][j][0], acc[i][j][1], af[buf][i], bf[buf][j]);
+    };
+    auto fold = [&](const int buf) {
+#pragma unroll
+      for (int i = 0; i < MT; i++) rel |= (uint32_t)__double2loint(af[buf][i]);
+#pragma unroll
+      for (int j = 0; j < NT; j++) rel |= (uint32_t)__double2loint(bf[buf][j]);
+    };
+#pragma unroll 1
+    for (int kh = 0; kh < TG_BK / 8; kh++) {
+      // k4 step 2 kh: fragments in buffer 0, step 2 kh + 1 requested into buffer 1
+      load_frags(1, stage_base, 2 * kh + 1);
+      mma(0);
       // Stage release.  An mbarrier arrive does not wait for the warp's outstanding ld.shared, and ptxas is free to
       // sink fragment loads and hoist the arrive, so "arrive after the loads were issued" is a race with the TMA refill
       // of the stage (generic-proxy reads vs async-proxy writes).  It showed once the ring stayed full and the
@@ -362,18 +377,22 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // `rel` ORs the low words of the fragments after the DMMAs that consumed them (no extra wait: the registers are
       // ready by then) plus, at the release point, the ones just requested for the last k4 step; `& p.zero` (a run-time
       // zero) keeps the chain alive through ptxas.  The arrive cannot issue before all those loads have returned.
-#pragma unroll
-      for (int i = 0; i < MT; i++) rel |= (uint32_t)__double2loint(af[cur][i]);
-#pragma unroll
-      for (int j = 0; j < NT; j++) rel |= (uint32_t)__double2loint(bf[cur][j]);
-      if (kk == TG_BK / 4 - 2) {
-#pragma unroll
-        for (int i = 0; i < MT; i++) rel |= (uint32_t)__double2loint(af[nxt][i]);
-#pragma unroll
-        for (int j = 0; j < NT; j++) rel |= (uint32_t)__double2loint(bf[nxt][j]);
+      fold(0);
+      if (kh == TG_BK / 8 - 1) {
+        fold(1);
         __syncwarp();
         if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s + (rel & (uint32_t)p.zero));
       }
+      // k4 step 2 kh + 1: buffer 1; the step after it (same stage, or the first of the next stage) goes into buffer 0
+      if (kh < TG_BK / 8 - 1) {
+        load_frags(0, stage_base, 2 * kh + 2);
+      } else if (has_next) {
+        const int s2 = (it0 + kt + 1) % TG_STAGES;
+        tg_mbar_wait(bar_base + 8 * s2, ((it0 + kt + 1) / TG_STAGES) & 1);
+        load_frags(0, smem_base + s2 * TG_STAGE_BYTES, 0);
+      }
+      mma(1);
+      fold(1);
     }
   };
   for (int kt = 0; kt < KT; kt++) {
@@ -437,6 +456,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   if (staggered && n == 0 && KT == 0 && warp == 0 && lane == 0) *stagger_go = 1;
   TG_STAMP(n, 3);
+  TG_CTA(2);
   // ---- epilogue: C fragment (row g, cols 2 tq, 2 tq + 1) -> 16-byte stores ----------------------
 #pragma unroll
   for (int i = 0; i < MT; i++) {
@@ -457,6 +477,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
   it0 += KT;
   TG_STAMP(n, 4);
+  TG_CTA(3);
   if (!p.sched) break;
   // next work item of this CTA: its id is valid once the first stage of the tile (or the end marker) has been posted
   tg_mbar_wait(bar_base + 8 * (it0 % TG_STAGES), (it0 / TG_STAGES) & 1);
