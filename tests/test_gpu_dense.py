@@ -406,6 +406,26 @@ def test_factor_and_inverse_properties_at_scale():
     assert abs(float(logdet) - float(torch.linalg.slogdet(A)[1])) < 1e-9 * n
 
 
+def test_batched_factor_and_inverse_fused_256_blocks():
+    """Batched problems (>= 8) factor their 256-blocks with the fused factor256_kernel by default: L, L^-1 and log|A| of
+    32 x (n = 512) and 9 x (n = 300, ragged: padded to 384, base-kernel path) against torch.linalg, plus the LAPACK-style
+    status of a batch with one non-PD problem."""
+    from fidelityfusion_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    for batch, n in ((32, 512), (9, 300), (8, 256)):
+        X = torch.randn(batch, n, n + 16, device=DEV, generator=gen)
+        A = X @ X.transpose(1, 2) / n + 0.25 * torch.eye(n, device=DEV)
+        L, M, logdet = ops.potrf_trtri(A)
+        Lr = torch.linalg.cholesky(A)
+        assert float((L - Lr).abs().max() / Lr.abs().max()) < 1e-12
+        assert float((M @ Lr - torch.eye(n, device=DEV)).abs().max()) < 1e-10
+        assert float((logdet - 2 * Lr.diagonal(dim1=1, dim2=2).log().sum(1)).abs().max()) < 1e-9 * n      # log|A|
+    A = torch.eye(512, device=DEV).repeat(16, 1, 1)
+    A[5, 300, 300] = -2.0
+    with pytest.raises(torch.linalg.LinAlgError):
+        ops.potrf_trtri(A)
+
+
 def test_c2_full_size_anchor_and_gradient_identity():
     """BASELINE config 2 at full size (N=8192, d=16): the NLL anchor recorded from the reference on CPU
      and gradient identities that need no CPU factorisation:

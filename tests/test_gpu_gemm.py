@@ -19,3 +19,14 @@ def test_gemm_all_modes(persist, n64):
         r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'check_gemm.py')], env=env, capture_output=True,
                            text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_factor256_kernel_all_modes():
+    """factor256_kernel (csrc/factor256.cuh: potrf + trtri of a 256-block in one launch) against torch.linalg.cholesky
+    and against the six-launch path it replaces, with and without the structural-zero skipping, single and batched
+    problems, sizes on both sides of the 256 / 512 block boundaries, and a non-PD block reported through info
+    (tools/f256_check.py runs FFGP_F256 = 0, 3, 2 in sub-processes: the switch is read once per process)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'f256_check.py')], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert r.stdout.count('non-PD detected') == 3, r.stdout[-4000:]

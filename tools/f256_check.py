@@ -8,15 +8,14 @@ if len(sys.argv) > 1 and sys.argv[1] == 'child':
     import torch
     from fidelityfusion_b200 import ops
     torch.manual_seed(0)
-    for n, batch in ((256, 1), (256, 5), (512, 3), (384, 2), (1024, 1), (300, 2), (512, 592), (2048, 1)):
+    for n, batch in ((256, 1), (256, 5), (512, 3), (384, 2), (1024, 1), (300, 2), (512, 296), (2048, 1)):
         X = torch.randn(batch, n, n + 8, dtype=torch.float64, device='cuda')
         A = X @ X.transpose(1, 2) / n + 0.5 * torch.eye(n, dtype=torch.float64, device='cuda')
         L, Mi, ld = ops.potrf_trtri(A)
         Lr = torch.linalg.cholesky(A)
         eL = float((L - Lr).abs().max() / Lr.abs().max())
         eM = float((Mi @ Lr - torch.eye(n, dtype=torch.float64, device='cuda')).abs().max())
-        ref = Lr.diagonal(dim1=1, dim2=2).log().sum(1)
-        eD = float(torch.minimum((ld - ref).abs(), (ld - 2 * ref).abs()).max())
+        eD = float((ld - 2 * Lr.diagonal(dim1=1, dim2=2).log().sum(1)).abs().max())      # log|A|
         for _ in range(2): ops.potrf_trtri(A, want_L=False, want_inv=False)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
