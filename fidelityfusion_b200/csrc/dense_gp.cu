@@ -707,7 +707,16 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   kp.K = w.A; kp.n1 = a.n; kp.n2 = a.n; kp.d = a.d; kp.np1 = w.np; kp.np2 = w.np; kp.ldk = w.np;
   kp.sK = (long long)w.np * w.np;
   kp.symmetric = 1; kp.lower_only = 1; kp.clamp = a.clamp;
-  kernel_matrix_kernel<<<dim3(w.np / 64, w.np / 64, nb), 256, 0, st>>>(kp);
+  trace_mark("start", 0, 0, st);
+  // the plain kernel case (no covariance term, d <= 16) goes through the lower-super-tile kernel; FFGP_KM128=0: general kernel
+  static int km128 = -1;
+  if (km128 < 0) { const char* e = getenv("FFGP_KM128"); km128 = (e && atoi(e) == 0) ? 0 : 1; }
+  if (km128 && kp.x1 && kp.amp && kp.w && !kp.sigma_add && a.d >= 1 && a.d <= 16 && nb <= 65535) {
+    const int tt = w.np / 128;
+    kernel_matrix_sym128_kernel<<<dim3(tt * (tt + 1) / 2, nb), 256, 0, st>>>(kp);
+  } else {
+    kernel_matrix_kernel<<<dim3(w.np / 64, w.np / 64, nb), 256, 0, st>>>(kp);
+  }
   FFGP_LAUNCHED();
   trace_mark("kernel_matrix", 0, 0, st);
   FactorCtx c{w.A, w.L, w.M, w.np, (long long)w.np * w.np, nb, w.logdet_part, w.nblk, info + b0, st};

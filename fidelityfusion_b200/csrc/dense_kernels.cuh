@@ -168,6 +168,117 @@ __global__ void __launch_bounds__(256) kernel_matrix_kernel(const KernelMatrixPa
   }
 }
 
+// Assembly of the symmetric kernel matrix of a factorisation (x1 == x2, lower part, padded to a multiple of 128 with an
+// identity tail, d <= 16, no sigma_add / offset): one CTA per LOWER 128 x 128 super-tile, its four 64 x 64 sub-tiles in a
+// rolled loop over the same code.  Why a second kernel: `ncu --set full` of kernel_matrix_kernel on BASELINE config 5
+// (gpurun_out/r02_c5_small_kernels.ncu-rep) shows it ISSUE-bound - 66 % issue-slot utilisation at 35 % FP64-pipe
+// utilisation, ~105 instructions per matrix entry of which ~30 are FP64 (the cross term on DMMA, one exp): the rest is
+// the per-entry bounds / diagonal / optional-term logic of the general kernel, the staging of the scaled inputs (redone
+// for every 64 x 64 tile) and 44 % of the grid being CTAs above the diagonal that exit at once.  Here the inputs of 128
+// rows and 128 columns are staged once per 16384 entries, interior super-tiles skip every per-entry check, and the grid
+// enumerates lower super-tiles only.
+__global__ void __launch_bounds__(256) kernel_matrix_sym128_kernel(const KernelMatrixParams p) {
+  constexpr int T = 128, S = 64, DC = 16, LD = DC + 4;
+  int t = blockIdx.x;
+  int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (ti * (ti + 1) / 2 > t) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  const int tj = t - ti * (ti + 1) / 2, b = blockIdx.y;
+  __shared__ double xs1[T][LD], xs2[T][LD];
+  __shared__ double nrm[2][T];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3;        // 2 x 4 warps, warp tile 32 x 16 of a 64 x 64 sub-tile
+  const int g = lane >> 2, tq = lane & 3;
+  const double* x = p.x1 + b * p.sx1;
+  const double* w = p.w + b * p.sw;
+  const int i0 = ti * T, j0 = tj * T, n = p.n1, d = p.d;
+  for (int e = tid; e < 2 * T * DC; e += 256) {
+    const int which = e / (T * DC), r = (e / DC) % T, k = e % DC;
+    const int gi = (which ? j0 : i0) + r;
+    double v = 0.0;
+    if (gi < n && k < d) v = x[(long long)gi * d + k] * w[k];
+    (which ? xs2 : xs1)[r][k] = v;
+  }
+  __syncthreads();
+  {
+    const int which = tid / T, r = tid % T;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DC; k++) { const double v = (which ? xs2 : xs1)[r][k]; s = fma(v, v, s); }
+    nrm[which][r] = s;
+  }
+  __syncthreads();
+  const double amp = p.amp[b * p.samp];
+  const double* dg = p.diag_add ? p.diag_add + b * p.sdiag : nullptr;
+  double* K = p.K + b * p.sK;
+  const bool interior = (i0 + T <= n) && (j0 + T <= n);
+  const int nkk = (d + 3) >> 2;                    // k4 steps that hold non-zero dimensions
+#pragma unroll 1
+  for (int st = 0; st < 4; st++) {
+    const int si = st >> 1, sj = st & 1;
+    if (ti == tj && sj > si) continue;             // above the diagonal
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+#pragma unroll 1
+    for (int kk = 0; kk < nkk; kk++) {
+      double af[4], bf[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) af[i] = xs1[si * S + wm * 32 + i * 8 + g][kk * 4 + tq];
+#pragma unroll
+      for (int j = 0; j < 2; j++) bf[j] = xs2[sj * S + wn * 16 + j * 8 + g][kk * 4 + tq];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    double kv[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          double sq = nrm[0][si * S + wm * 32 + i * 8 + g] + nrm[1][sj * S + wn * 16 + j * 8 + tq * 2 + e] - 2.0 * acc[i][j][e];
+          if (p.clamp) sq = fmax(sq, 0.0);
+          kv[i][j][e] = amp * exp_nonpos(-0.5 * sq);
+        }
+    const bool diag_sub = (ti == tj) && (si == sj);
+    if (interior && !diag_sub) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int gi = i0 + si * S + wm * 32 + i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const int gj = j0 + sj * S + wn * 16 + j * 8 + tq * 2;
+          *reinterpret_cast<double2*>(K + (long long)gi * p.ldk + gj) = make_double2(kv[i][j][0], kv[i][j][1]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int gi = i0 + si * S + wm * 32 + i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const int gj0 = j0 + sj * S + wn * 16 + j * 8 + tq * 2;
+          double out[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int gj = gj0 + e;
+            double v = kv[i][j][e];
+            if (gi < n && gj < n) { if (dg && gi == gj) v += dg[gi]; }
+            else v = (gi == gj) ? 1.0 : 0.0;
+            out[e] = v;
+          }
+          *reinterpret_cast<double2*>(K + (long long)gi * p.ldk + gj0) = make_double2(out[0], out[1]);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // 128x128 diagonal block: L = chol(A_block) and M = L^-1 in ONE right-looking sweep.
 // The forward substitution L M = I is carried along with the factorisation (the rank-8 update
