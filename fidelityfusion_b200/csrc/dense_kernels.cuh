@@ -899,8 +899,11 @@ __host__ __device__ inline size_t grad_smem_doubles(int d) {
 // dimension by dimension twice (5 d + 45 FP64 instructions per pair, FP64-FMA bound: 0.88 ms per 512 problems of
 // N = 512, d = 8, profiles/r01_launches_c5_v6.csv); this one needs about 35 per pair independent of d.
 // GOUT: also write the full symmetric dNLL/dSigma (covariance-input mode); kept out of the common instantiation.
+#ifndef GRAD_MIN_CTAS
+#define GRAD_MIN_CTAS 3
+#endif
 template <bool GOUT>
-__global__ void __launch_bounds__(256) grad_contract_kernel(const GradParams p) {
+__global__ void __launch_bounds__(256, GRAD_MIN_CTAS) grad_contract_kernel(const GradParams p) {
   extern __shared__ __align__(16) double gsm[];
   const int b = blockIdx.y;
   int t = blockIdx.x;
