@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <type_traits>
 #include "gemm_dmma.cuh"
 
 namespace ffgp {
@@ -533,12 +534,16 @@ __device__ __forceinline__ int base_factor_smem(double* __restrict__ sm, const i
       }
     }
     BASE_STAMP(p, 2);
-    for (int rq = warp - 1; rq < nquad; rq += 7) {
+    // A row group only has entries in the 32-wide groups of virtual columns that start at or below its last row
+    // (v <= i): the groups beyond are all masked lanes - at panel 0 more than half of the FMAs of the original
+    // all-groups loop (profiles/r02_base_kernel_timeline_v3.txt).  One body per group count, selected per row group.
+    auto quad = [&](auto qn_tag, const int rq) {
+      constexpr int QN = decltype(qn_tag)::value;
       const int i0 = r0 + 4 * rq;
-      double cacc[4][QV];
-      int idx[4][QV];
+      double cacc[4][QN];
+      int idx[4][QN];
 #pragma unroll
-      for (int q = 0; q < QV; q++) {
+      for (int q = 0; q < QN; q++) {
         const int v = lane + 32 * q;
         const bool isR = v < r0;
 #pragma unroll
@@ -551,9 +556,6 @@ __device__ __forceinline__ int base_factor_smem(double* __restrict__ sm, const i
           cacc[a][q] = T[idx[a][q]];
         }
       }
-      // the 32 panel entries of the quad's rows are requested up front (broadcast loads, all in flight together): with
-      // them inside the kk loop every rank-1 step started with a shared-memory round trip and a quad took ~1150 clk
-      // for 128 FMAs per lane (profiles/r02_base_kernel_timeline_v3.txt)
       double av[4][8];
 #pragma unroll
       for (int a = 0; a < 4; a++)
@@ -564,12 +566,19 @@ __device__ __forceinline__ int base_factor_smem(double* __restrict__ sm, const i
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int q = 0; q < QV; q++) cacc[a][q] = fma(av[a][kk], bv[kk][q], cacc[a][q]);
+          for (int q = 0; q < QN; q++) cacc[a][q] = fma(av[a][kk], bv[kk][q], cacc[a][q]);
       }
 #pragma unroll
-      for (int q = 0; q < QV; q++)
+      for (int q = 0; q < QN; q++)
 #pragma unroll
         for (int a = 0; a < 4; a++) T[idx[a][q]] = cacc[a][q];
+    };
+    for (int rq = warp - 1; rq < nquad; rq += 7) {
+      const int qn = min(QV, ((r0 + 4 * rq + 3) >> 5) + 1);
+      if (QV == 4 && qn == 4) quad(std::integral_constant<int, QV>{}, rq);
+      else if (QV == 4 && qn == 3) quad(std::integral_constant<int, (QV > 2 ? 3 : QV)>{}, rq);
+      else if (qn == 2) quad(std::integral_constant<int, 2>{}, rq);
+      else quad(std::integral_constant<int, 1>{}, rq);
     }
     BASE_STAMP(p, 3);
   }
