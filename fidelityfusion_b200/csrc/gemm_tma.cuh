@@ -27,6 +27,22 @@
 
 namespace ffgp {
 
+// Stage release of the operand ring.  History: an mbarrier arrive does not wait for the warp's outstanding ld.shared, and
+// ptxas is free to sink fragment loads and hoist the arrive, so "arrive after the loads were ISSUED" is a race with the
+// TMA refill of the stage (generic-proxy reads vs async-proxy writes).  It showed once the ring stayed full and the
+// load/store queue was backed up (persistent grid + 64 global loads of C per thread at the start of a tile): one warp's
+// last-loaded A / B fragments were overwritten before they were served, ~1 tile in 500 wrong (tools/diag_stage_release.py).
+//   TG_RELEASE_LATE = 0  (round 1) early release, one k4 step before the end of the stage, kept correct by making the
+//                        barrier ADDRESS data-dependent on every fragment read from the stage (`rel & p.zero`, a run-time
+//                        zero): works, but it is a scheduling trick, not a memory-model guarantee;
+//   TG_RELEASE_LATE = 1  (default) release after the DMMAs of the stage's last k4 step have issued: a DMMA cannot issue
+//                        before the ld.shared feeding its operands have returned, a warp issues in order and the
+//                        compiler keeps the order of the asm volatile statements - provably ordered, 24 LOP3 per k4 step
+//                        fewer, and the stage is handed back ~500 clk later out of a 6-stage ring
+//                        (A/B on one box: profiles/r02_c5_experiments.txt).
+#ifndef TG_RELEASE_LATE
+#define TG_RELEASE_LATE 1
+#endif
 constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 16, TG_STAGES = 6;
 constexpr int TG_CONSUMER_WARPS = 8;
 constexpr int TG_THREADS = (TG_CONSUMER_WARPS + 4) * 32;             // 2 consumer warpgroups + 1 producer warpgroup
@@ -368,21 +384,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // k4 step 2 kh: fragments in buffer 0, step 2 kh + 1 requested into buffer 1
       load_frags(1, stage_base, 2 * kh + 1);
       mma(0);
-      // Stage release.  An mbarrier arrive does not wait for the warp's outstanding ld.shared, and ptxas is free to
-      // sink fragment loads and hoist the arrive, so "arrive after the loads were issued" is a race with the TMA refill
-      // of the stage (generic-proxy reads vs async-proxy writes).  It showed once the ring stayed full and the
-      // load/store queue was backed up (persistent grid + 64 global loads of C per thread at the start of a tile): one
-      // warp's last-loaded A / B fragments were overwritten before they were served, ~1 tile in 500 wrong
-      // (tools/diag_stage_release.py).  So the barrier ADDRESS is made data-dependent on EVERY fragment read from this stage:
-      // `rel` ORs the low words of the fragments after the DMMAs that consumed them (no extra wait: the registers are
-      // ready by then) plus, at the release point, the ones just requested for the last k4 step; `& p.zero` (a run-time
-      // zero) keeps the chain alive through ptxas.  The arrive cannot issue before all those loads have returned.
+#if !TG_RELEASE_LATE
       fold(0);
       if (kh == TG_BK / 8 - 1) {
         fold(1);
         __syncwarp();
         if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s + (rel & (uint32_t)p.zero));
       }
+#endif
       // k4 step 2 kh + 1: buffer 1; the step after it (same stage, or the first of the next stage) goes into buffer 0
       if (kh < TG_BK / 8 - 1) {
         load_frags(0, stage_base, 2 * kh + 2);
@@ -392,8 +401,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         load_frags(0, smem_base + s2 * TG_STAGE_BYTES, 0);
       }
       mma(1);
+#if !TG_RELEASE_LATE
       fold(1);
+#endif
     }
+#if TG_RELEASE_LATE
+    // Stage release AFTER the DMMAs of the stage's last k4 step (program order between the asm volatile statements is
+    // kept by the compiler, a warp issues in order, and a DMMA cannot issue before the ld.shared that feed its operands
+    // have returned): every fragment load of this stage has completed when the arrive issues, so the TMA refill
+    // (async-proxy write) cannot overtake a generic-proxy read of the stage.  No data-dependency trick needed.
+    (void)rel; (void)fold;
+    __syncwarp();
+    if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s);
+#endif
   };
   for (int kt = 0; kt < KT; kt++) {
 #ifdef FFGP_TG_TRACE
