@@ -622,7 +622,9 @@ static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int 
     // beta = 1 accumulation: one launch with K up to h keeps every SM busy for ~100 us per tile and stalled the panel
     // chain by 1.7 ms (profiles/r01_timeline_c2_v1.txt, steps 19-20); with 512-deep tiles an SM frees up every ~7 us.
     g_trace_label = "bg:W";
-    const int KC = 512;
+    static int KCv = -1;                             // FFGP_BG_KC: K chunk of the background W product (256 / 512 / 1024)
+    if (KCv < 0) { const char* ev = getenv("FFGP_BG_KC"); KCv = ev ? atoi(ev) : 512; if (KCv < 128 || KCv % 128) KCv = 512; }
+    const int KC = KCv;
     for (int s0 = 0; s0 < h && e2 == cudaSuccess; s0 += KC) {
       const int kc = std::min(KC, h - s0);
       // columns [s0, s0 + kc): first touch, the chunk's own lower-triangular block of M11 (K range starts at the column)

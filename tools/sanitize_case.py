@@ -1,6 +1,6 @@
 """Small end-to-end cases for compute-sanitizer (memcheck / racecheck / synccheck): a batched C5-shaped evaluation
 (NLL + gradient + prediction, 12 x N = 300 -> padded 384, exercising the base kernel, the TMA and cp.async GEMMs, the
-vector kernels and the gradient contraction), a single dense evaluation with D > 8 (GEMM right-hand sides), the
+vector kernels and the gradient contraction), a second batch of 8 x N = 256 through the fused 256-block kernel and the lower-super-tile kernel-matrix kernel, a single dense evaluation with D > 8 (GEMM right-hand sides), the
 Kronecker path (mode products, mode Gram, core, one-sided Jacobi in 1-, 2- and 8-CTA clusters) and the row matcher."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,6 +17,13 @@ x = torch.rand(B, n, d, generator=g).cuda(); y = torch.randn(B, n, 1, generator=
 out = batched_cigp_eval(x, y, (torch.rand(B, d, generator=g) + 0.5).cuda(), torch.ones(B).cuda(), torch.rand(B, generator=g).cuda(),
                         torch.rand(B, ns, d, generator=g).cuda())
 print('batched nll', float(out['nll'].sum()))
+# round 2 kernels: 8 problems of n = 256 (np = 256: one factor256_kernel launch per problem, kernel_matrix_sym128_kernel, the
+# symmetric / triangular bodies of the rolled TMA GEMM main loop in S = M^T M) - NLL + gradient + prediction
+B2, n2 = 8, 256
+x2 = torch.rand(B2, n2, d, generator=g).cuda(); y2 = torch.randn(B2, n2, 1, generator=g).cuda()
+out2 = batched_cigp_eval(x2, y2, (torch.rand(B2, d, generator=g) + 0.5).cuda(), torch.ones(B2).cuda(), torch.rand(B2, generator=g).cuda(),
+                         torch.rand(B2, ns, d, generator=g).cuda())
+print('batched f256 nll', float(out2['nll'].sum()))
 m = cigp(ARDKernel(5), 1.0).cuda()
 xx = torch.rand(200, 5, generator=g).cuda(); yy = torch.randn(200, 24, generator=g).cuda()
 (-m.negative_log_likelihood(xx, yy)).backward()
