@@ -285,7 +285,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const bool init_from_c = (beta != 0.0) && (alpha != 0.0);
   const int role = wm * 4 + wn;
   double acc[MT][NT][2];
-  int it0 = 0;                                     // k-steps consumed before this tile (the stage ring runs on across tiles)
+  // ring position of the NEXT k-step to consume (the stage ring runs on across tiles): stage index and phase parity are
+  // carried incrementally - `it % TG_STAGES` and `it / TG_STAGES` per k-step were two multiply-high sequences in front of the
+  // first DMMA of every k-step
+  int cs = 0;
+  uint32_t cph = 0;
   int w = blockIdx.x;
   // Stagger experiment (FFGP_STAGGER = k-steps, default 0 = off; persistent grid only).  Warps w and w + 4 share an SM
   // sub-partition; started together, both reach every tile's epilogue + accumulator init (~4.4k clk per tile) at the same
@@ -346,8 +350,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   TG_STAMP(n, 1);
   if (KT > 0) {
-    tg_mbar_wait(bar_base + 8 * (it0 % TG_STAGES), (it0 / TG_STAGES) & 1);
-    load_frags(0, smem_base + (it0 % TG_STAGES) * TG_STAGE_BYTES, 0);
+    tg_mbar_wait(bar_base + 8 * cs, cph);
+    load_frags(0, smem_base + cs * TG_STAGE_BYTES, 0);
   }
   TG_STAMP(n, 2);
   TG_CTA(1);
@@ -362,8 +366,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   // for 17.4k clk of DMMA issue (profiles/r02_lauum_icache.txt).  Halving every body brings both working sets under it.
   auto kt_body = [&](auto lv, int kt) {
     using Lv = decltype(lv);
-    const int s = (it0 + kt) % TG_STAGES;
+    const int s = cs;
     const uint32_t stage_base = smem_base + s * TG_STAGE_BYTES;
+    const int s2 = (cs + 1 == TG_STAGES) ? 0 : cs + 1;
+    const uint32_t ph2 = (cs + 1 == TG_STAGES) ? cph ^ 1u : cph;
     const bool has_next = kt + 1 < KT;
     uint32_t rel = 0;
     auto mma = [&](const int buf) {
@@ -396,8 +402,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (kh < TG_BK / 8 - 1) {
         load_frags(0, stage_base, 2 * kh + 2);
       } else if (has_next) {
-        const int s2 = (it0 + kt + 1) % TG_STAGES;
-        tg_mbar_wait(bar_base + 8 * s2, ((it0 + kt + 1) / TG_STAGES) & 1);
+        tg_mbar_wait(bar_base + 8 * s2, ph2);
         load_frags(0, smem_base + s2 * TG_STAGE_BYTES, 0);
       }
       mma(1);
@@ -414,7 +419,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncwarp();
     if (lane == 0) tg_mbar_arrive(bar_base + 64 + 8 * s);
 #endif
+    cs = s2;
+    cph = ph2;
   };
+  if (!sym_diag && tri_mode == 0 && !staggered) {
+    // dense tile (every long-K tile of the single large factorisation): no per-k-step variant dispatch
+#pragma unroll 1
+    for (int kt = 0; kt < KT; kt++) kt_body(TgLive<0, MT, 0, NT, -1>{}, kt);
+  } else
   for (int kt = 0; kt < KT; kt++) {
 #ifdef FFGP_TG_TRACE
     if (n == 0 && kt < 8) TG_STAMP(24 + kt, 0);          // first tile: start of every k-step (rows 24.. of the trace)
@@ -495,12 +507,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       *dst = v;
     }
   }
-  it0 += KT;
   TG_STAMP(n, 4);
   TG_CTA(3);
   if (!p.sched) break;
   // next work item of this CTA: its id is valid once the first stage of the tile (or the end marker) has been posted
-  tg_mbar_wait(bar_base + 8 * (it0 % TG_STAGES), (it0 / TG_STAGES) & 1);
+  tg_mbar_wait(bar_base + 8 * cs, cph);
   w = tile_ring[(n + 1) % TG_TILE_RING];
   TG_STAMP(n, 5);
   if (w < 0) break;
