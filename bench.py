@@ -29,7 +29,7 @@ B_C5, N_C5, D_C5, NS_C5 = 4096, 512, 8, 64
 F_ALG_C5 = N_C5 ** 3 + 4 * N_C5 ** 2 * D_C5 + 4 * N_C5 ** 2 * 1            # 1.437e8 FLOP / GP
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE S = M^T M launch of the dominant kernel at N=8192 (ncu,
 # profiles/r01_metrics_c2_v1.txt: 2 launches read 2794 MB and wrote 460 MB); algorithmic bytes 8 N^2 = 537 MB
-TRAFFIC_LAUUM_BYTES = 1.814e9     # dram read 1.588 GB + write 0.226 GB per launch, profiles/r01_ncu_gemm_tma_lauum_v10.txt
+TRAFFIC_LAUUM_BYTES = 1.788e9     # dram read 1.561 GB + write 0.227 GB per launch, profiles/r02_ncu_gemm_tma_lauum_final.txt
 
 
 def c2_inputs(torch):
