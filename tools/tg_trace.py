@@ -34,6 +34,8 @@ nb = 8 * 148
 run('dense 128-cube  A[i][p] B[j][p]', 1, 1, 0, 128, 128, 128, nb)
 run('K_LE_COL 128 (L21 = A21 M11^T)', 1, 1, 2, 128, 128, 128, nb)
 run('K_LE_ROW 128 (T = M22 L21)', 1, 0, 1, 128, 128, 128, nb)
+run('K_GE_ROW 128 (S = M^T M block)', 0, 0, 4, 128, 128, 128, nb)
+run('K_GE_COL 128 (M21 = -T M11)', 1, 0, 3, 128, 128, 128, nb)
 run('dense 256-deep tiles', 1, 1, 0, 256, 256, 256, 2 * 148)
 run('syrk lower 256 beta=1', 1, 1, 0, 256, 256, 256, 3 * 148, lower=1, beta=1.0)
 run('S = M^T M 512 lower', 0, 0, 4, 512, 512, 512, 148, lower=1)
