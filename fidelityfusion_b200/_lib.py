@@ -64,6 +64,8 @@ def lib():
     _sig(L.ffgp_mode_gram_scratch_bytes, sz, [ll, ll, i, i])
     _sig(L.ffgp_mode_gram_f64, i, [vp, vp, vp, ll, ll, i, i, vp, sz, vp])
     _sig(L.ffgp_kron_scale_f64, i, [vp, vp, ctypes.POINTER(ctypes.c_int), i, i, i, vp, ctypes.c_double, vp, vp])
+    _sig(L.ffgp_kron_ck_scratch_bytes, sz, [i])
+    _sig(L.ffgp_kron_ck_f64, i, [vp, ctypes.POINTER(ctypes.c_int), i, i, vp, ctypes.c_double, vp, vp, sz, vp])
     _sig(L.ffgp_syevj_workspace_bytes, sz, [i, i])
     _sig(L.ffgp_syevj_f64, i, [vp, i, i, vp, vp, vp, sz, vp, vp])
     _sig(L.ffgp_kron_core_scratch_bytes, sz, [ll])

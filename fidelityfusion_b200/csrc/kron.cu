@@ -644,6 +644,42 @@ __global__ void __launch_bounds__(256) kron_scale_kernel(const double* __restric
   }
 }
 
+// c_k[j] = sum over the other modes' indices of  P / (lambda_k[j] P + tau),  P = prod_{m != k} lambda_m[i_m]:
+// the diagonal weights of the closed-form gradient w.r.t. mode k's kernel matrix (tensorly_compat._KronNLL.backward).
+// It depends on the eigenvalues only, so it is a pure reduction - the first version materialised W_k = P / A as a full
+// tensor (kron_scale) and contracted it with a tensor of ones (mode_gram): 3 passes over 33 MB per mode at the C4 size.
+// grid (n_k, S): block (j, y) sums its slice of the other-index space in a fixed order; kron_ck_finish adds the S partials.
+__global__ void __launch_bounds__(256) kron_ck_kernel(const double* __restrict__ lam, KronSizes other, int lam_k_off,
+                                                      const double* __restrict__ noise_inv, double add, long long other_total,
+                                                      double* __restrict__ part) {
+  __shared__ double red[8];
+  const double tau = (noise_inv ? noise_inv[0] : 0.0) + add;
+  const int j = blockIdx.x, S = gridDim.y;
+  const double lk = lam[lam_k_off + j];
+  double acc = 0.0;
+  for (long long o = (long long)blockIdx.y * 256 + threadIdx.x; o < other_total; o += (long long)S * 256) {
+    const double P = kron_lambda_prod(o, other, lam, -1);
+    acc += P / fma(lk, P, tau);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int k = 0; k < 8; k++) v += red[k];
+    part[(long long)j * S + blockIdx.y] = v;
+  }
+}
+__global__ void kron_ck_finish_kernel(const double* __restrict__ part, int n, int S, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double v = 0.0;
+  for (int y = 0; y < S; y++) v += part[(long long)j * S + y];
+  out[j] = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Jacobi eigensolver (cyclic, round-robin parallel ordering).  One CTA per matrix.
 //   a: n x lda working copy of A (shared memory when n <= 128, else global), vt: rows = eigenvectors
@@ -1204,6 +1240,35 @@ int ffgp_kron_scale_f64(const double* in, const double* lambdas, const int* size
     kron_scale_kernel<true><<<nb, 256, 0, (cudaStream_t)stream>>>(in, lambdas, s, skip_mode, divide_by_A, noise_inv, add_scalar, total, out);
   else
     kron_scale_kernel<false><<<nb, 256, 0, (cudaStream_t)stream>>>(in, lambdas, s, skip_mode, divide_by_A, noise_inv, add_scalar, total, out);
+  ++ffgp::g_launches;
+  FFGP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t ffgp_kron_ck_scratch_bytes(int n_k) { return n_k > 0 ? (size_t)n_k * 64 * sizeof(double) + 256 : 0; }
+
+int ffgp_kron_ck_f64(const double* lambdas, const int* sizes_host, int nmodes, int mode, const double* noise_inv,
+                     double add_scalar, double* out, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!lambdas || !sizes_host || !out || !scratch) return fail(-1, "ffgp_kron_ck_f64: null pointer%s", "");
+  if (nmodes < 2 || nmodes > 8 || mode < 0 || mode >= nmodes) return fail(-2, "ffgp_kron_ck_f64: 2..8 modes, 0 <= mode < nmodes%s", "");
+  const int nk = sizes_host[mode];
+  if (nk <= 0 || scratch_bytes < ffgp_kron_ck_scratch_bytes(nk)) return fail(-3, "ffgp_kron_ck_f64: scratch too small%s", "");
+  KronSizes all = make_sizes(sizes_host, nmodes), other;
+  memset(&other, 0, sizeof(other));
+  long long other_total = 1;
+  for (int m = 0; m < nmodes; m++) {
+    if (m == mode) continue;
+    other.n[other.nmodes] = all.n[m];
+    other.off[other.nmodes] = all.off[m];
+    other.nmodes++;
+    other_total *= all.n[m];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = (int)std::max<long long>(1, std::min<long long>(64, (other_total + 2047) / 2048));
+  kron_ck_kernel<<<dim3(nk, S), 256, 0, st>>>(lambdas, other, all.off[mode], noise_inv, add_scalar, other_total, (double*)scratch);
+  ++ffgp::g_launches;
+  FFGP_CUDA(cudaGetLastError());
+  kron_ck_finish_kernel<<<(nk + 127) / 128, 128, 0, st>>>((const double*)scratch, nk, S, out);
   ++ffgp::g_launches;
   FFGP_CUDA(cudaGetLastError());
   return 0;

@@ -228,6 +228,21 @@ def _kron_scale(inp, lam_cat, sizes, skip, divide_by_A, tau_t, add, dev):
     return out
 
 
+def _kron_ck(lam_cat, sizes, k, tau_t, add, dev):
+    """c_k[j] = sum_{i_k = j} prod_{m != k} lambda_m / A: a reduction over the eigenvalues only (ffgp_kron_ck_f64)."""
+    L = B.lib()
+    nk = int(sizes[k])
+    if len(sizes) < 2:                                   # single mode: c_0[j] = 1 / (lambda_0[j] + tau)
+        return 1.0 / (lam_cat + tau_t + add)
+    out = torch.empty(nk, dtype=torch.float64, device=dev)
+    sb = L.ffgp_kron_ck_scratch_bytes(nk)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+    rc = L.ffgp_kron_ck_f64(B.ptr(lam_cat), _sizes_arr(sizes), len(sizes), int(k), B.ptr(tau_t), float(add), B.ptr(out),
+                            B.ptr(scratch), sb, B.stream_ptr())
+    B.check(rc, 'ffgp_kron_ck_f64')
+    return out
+
+
 class _KronNLL(torch.autograd.Function):
     """S = kron(K_0..K_M) + tau I;  returns (0.5*log|S| + 0.5*vec(Y)^T S^-1 vec(Y),  A,  g = S^-1 vec(Y)).
     Gradient (closed form, no differentiation through eigh):
@@ -278,10 +293,7 @@ class _KronNLL(torch.autograd.Function):
             if not ctx.needs_input_grad[3 + k]:
                 gKs.append(None)
                 continue
-            Wk = _kron_scale(None, lam_cat, sizes, k, 1, tau_t, add, dev)            # prod_{m!=k} lambda_m / A
-            ones_shape = list(sizes)
-            ones_shape[k] = 1
-            c_k = _mode_gram_raw(Wk, torch.ones(ones_shape, dtype=torch.float64, device=dev), k).reshape(-1)
+            c_k = _kron_ck(lam_cat, sizes, k, tau_t, add, dev)                       # sum_{i_k=j} prod_{m!=k} lambda_m / A
             hk = _kron_scale(h, lam_cat, sizes, k, 0, tau_t, add, dev)               # h o prod_{m!=k} lambda_m
             Qk = _mode_gram_raw(h, hk, k)
             Mk = (torch.diag(c_k) - Qk).contiguous()

@@ -258,6 +258,12 @@ int ffgp_kron_core_f64(const double* T1, const double* lambdas, const int* sizes
                        void* stream);
 int ffgp_kron_scale_f64(const double* in, const double* lambdas, const int* sizes_host, int nmodes, int skip_mode,
                         int divide_by_A, const double* noise_inv, double add_scalar, double* out, void* stream);
+/* c_k[j] = sum over the other modes' indices of prod_{m != mode} lambda_m / A (the diagonal weights of the closed-form
+ * gradient of the Kronecker objective w.r.t. mode `mode`'s kernel matrix, replacing autograd through torch.linalg.eigh in
+ * hogp.py:18-22,171-198): a reduction over the eigenvalues only, no pass over the data tensor.  out[sizes[mode]]. */
+size_t ffgp_kron_ck_scratch_bytes(int n_k);
+int ffgp_kron_ck_f64(const double* lambdas, const int* sizes_host, int nmodes, int mode, const double* noise_inv,
+                     double add_scalar, double* out, void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -323,3 +323,28 @@ def test_c4_full_size_kronecker_properties():
         h.noise_box.value.sub_(2 * eps)
         dn = h.compute_loss(x, Y).item()
     assert abs((up - dn) / (2 * eps) - g0) <= 1e-6 * max(abs(g0), 1e-3)
+
+
+def test_kron_ck_reduction_matches_the_materialised_weights():
+    """ffgp_kron_ck_f64 (c_k from the eigenvalues alone) against the first formulation: W_k = prod_{m != k} lambda_m / A as a
+    full tensor (ffgp_kron_scale_f64) contracted with ones over the other modes, and against a plain torch evaluation."""
+    from fidelityfusion_b200 import tensorly_compat as tl
+    gen = torch.Generator().manual_seed(11)
+    for sizes in ([128, 32, 32, 16], [40, 6, 5], [7, 3], [16, 8, 8, 4, 2]):
+        lams = [torch.rand(n, generator=gen, dtype=torch.float64) * 3 + 1e-3 for n in sizes]
+        lam_cat = torch.cat(lams).to(DEV)
+        tau = torch.tensor([0.37], dtype=torch.float64, device=DEV)
+        add = 0.05
+        kron = lams[0]
+        for l in lams[1:]:
+            kron = torch.outer(kron.reshape(-1), l).reshape(-1)
+        A = kron.reshape(sizes) + 0.37 + add
+        for k in range(len(sizes)):
+            ck = tl._kron_ck(lam_cat, sizes, k, tau, add, DEV).cpu()
+            shape = [1] * len(sizes); shape[k] = sizes[k]
+            W = (kron.reshape(sizes) / lams[k].reshape(shape)) / A
+            ref = W.movedim(k, 0).reshape(sizes[k], -1).sum(1)
+            assert rel_err(ck, ref) < 1e-13
+            Wk = tl._kron_scale(None, lam_cat, sizes, k, 1, tau, add, DEV)
+            old = Wk.movedim(k, 0).reshape(sizes[k], -1).sum(1).cpu()
+            assert rel_err(ck, old) < 1e-13
