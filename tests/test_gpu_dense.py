@@ -363,6 +363,30 @@ def test_c5_full_size_batch_vs_oracle_subset():
         assert rel_err(out['mean'][b].cpu(), om) < TOL and rel_err(out['var'][b].cpu(), oc.diag()) < TOL
 
 
+def test_batched_ragged_sizes_through_the_fused_blocks_vs_oracle():
+    """Batched problems (>= 8, so the fused 256-block kernel and the lower-super-tile kernel-matrix kernel run) whose
+    size is NOT a multiple of the block sizes: n = 500 (padded to 512: identity tail inside the last 128-block and the
+    last super-tile), n = 260 (padded to 384: base-kernel path, edge super-tiles), d = 3 and 16, two outputs."""
+    from fidelityfusion_b200.batched import batched_cigp_eval
+    for Bn, n, d, ns in ((9, 500, 3, 7), (8, 260, 16, 5)):
+        gen = torch.Generator().manual_seed(900 + n)
+        x = torch.rand(Bn, n, d, generator=gen)
+        y = torch.sin(2 * x.sum(-1, keepdim=True)) + 0.1 * torch.randn(Bn, n, 1, generator=gen)
+        ls = torch.exp(torch.rand(Bn, d, generator=gen) - 0.5)
+        lb = torch.rand(Bn, generator=gen) * 2
+        sv = torch.ones(Bn)
+        xs = torch.rand(Bn, ns, d, generator=gen)
+        out = batched_cigp_eval(x.to(DEV), y.to(DEV), ls.to(DEV), sv.to(DEV), lb.to(DEV), xs.to(DEV))
+        for b in (0, Bn - 1):
+            loss, gr = O.cigp_ard_nll_and_grads(x[b], y[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+            assert abs(out['nll'][b].item() - loss) <= TOL * abs(loss)
+            assert rel_err(out['g_length_scales'][b].cpu(), gr['length_scales']) < TOL
+            assert rel_err(out['g_signal_variance'][b].cpu().reshape(1), gr['signal_variance']) < TOL
+            assert rel_err(out['g_log_beta'][b].cpu().reshape(1), gr['log_beta']) < TOL
+            om, oc = O.cigp_ard_predict(x[b], y[b], xs[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+            assert rel_err(out['mean'][b].cpu(), om) < TOL and rel_err(out['var'][b].cpu(), oc.diag()) < TOL
+
+
 def test_not_positive_definite_raises_linalg_error():
     from fidelityfusion_b200 import ops
     y = torch.randn(40, 1, device=DEV)
@@ -412,7 +436,7 @@ def test_batched_factor_and_inverse_fused_256_blocks():
     status of a batch with one non-PD problem."""
     from fidelityfusion_b200 import ops
     gen = torch.Generator(device=DEV).manual_seed(7)
-    for batch, n in ((32, 512), (9, 300), (8, 256)):
+    for batch, n in ((32, 512), (9, 300), (8, 256), (10, 500)):      # 500 -> 512: fused 256-blocks with an identity tail
         X = torch.randn(batch, n, n + 16, device=DEV, generator=gen)
         A = X @ X.transpose(1, 2) / n + 0.25 * torch.eye(n, device=DEV)
         L, M, logdet = ops.potrf_trtri(A)
