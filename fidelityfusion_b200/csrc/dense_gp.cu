@@ -432,11 +432,34 @@ static int outer_nb() {
   return g_outer_nb;
 }
 
-// `at_half` (optional) is called once, right after every block column of the LEADING HALF of the matrix is final
-// (its panel factored and its rows below solved): from then on L[:, 0:np/2] and the diagonal-block inverses of the
-// leading half no longer change.
+// Panel widths of the look-ahead sweep of ONE large problem (FFGP_NB_EARLY = e, FFGP_NB_LATE = l, in sixteenths of the
+// matrix): columns [0, e np/16) in 512-wide panels (a step there is bound by its trailing update, and a 512-deep tile
+// reads and writes C half as often per FLOP), columns [l np/16, np) in 128-wide panels (a step there is bound by the
+// serial chain colupd -> diagonal block -> TRSM, which is shorter for a narrower panel), NB in between.
+// Defaults 0 / 16 = constant NB (profiles/r02_c2_panel_widths.txt).
+struct PanelWidths {
+  int nb = 256, early_until = 0, late_from = 1 << 30;
+  int at(int c0) const { return c0 < early_until ? 512 : (c0 >= late_from ? BASE_N : nb); }
+  int min_width() const { return late_from < (1 << 30) ? BASE_N : nb; }
+};
+static PanelWidths panel_widths(int np, int NB, bool single) {
+  PanelWidths w;
+  w.nb = NB;
+  static int early = -1, late = -1;
+  if (early < 0) { const char* e = getenv("FFGP_NB_EARLY"); early = e ? atoi(e) : 0; if (early < 0 || early > 16) early = 0; }
+  if (late < 0) { const char* e = getenv("FFGP_NB_LATE"); late = e ? atoi(e) : 16; if (late < 0 || late > 16) late = 16; }
+  if (!single || NB != 256 || np % 512 != 0 || np < 2048) return w;
+  const int eu = (int)((long long)np * early / 16), lf = (int)((long long)np * late / 16);
+  if (early > 0 && eu % 512 == 0 && eu <= lf) w.early_until = eu;
+  if (late < 16 && lf % NB == 0) w.late_from = lf;
+  return w;
+}
+
+// `at_cols(q)` (optional) is called after every step with the number q of leading columns whose block columns are
+// final (panel factored and the rows below it solved): from then on L[:, 0:q] and the diagonal-block inverses of
+// those columns no longer change.
 template <class Hook>
-static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahead, Hook at_half) {
+static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahead, Hook at_cols) {
   cudaError_t e;
   int NB = outer_nb();
   if (np % NB != 0) NB = BASE_N;
@@ -445,41 +468,45 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
   if (lookahead && nblk > 2) {
     if ((e = get_aux(&aux)) != cudaSuccess) return e;
   }
+  const PanelWidths pw = panel_widths(np, NB, aux != nullptr);
   FactorCtx ca = c;                 // context of the panel (side) stream
   if (aux) ca.st = aux->st;
-  auto at = [&](int bi, int bj) { return (long long)bi * NB * c.ld + (long long)bj * NB; };
-  // block column 0
-  if ((e = factor_rec(c, 0, NB)) != cudaSuccess) return e;
-  if (nblk > 1) {
-    if ((e = gemm(true, true, c.A + at(1, 0), c.ld, c.sb, c.M + at(0, 0), c.ld, c.sb, c.L + at(1, 0), c.ld, c.sb,
-                  np - NB, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, c.st)) != cudaSuccess) return e;
+  auto at = [&](int i, int j) { return (long long)i * c.ld + j; };
+  // first panel
+  int c0 = 0, w0 = pw.at(0);
+  if ((e = factor_rec(c, 0, w0)) != cudaSuccess) return e;
+  if (w0 < np) {
+    if ((e = gemm(true, true, c.A + at(w0, 0), c.ld, c.sb, c.M + at(0, 0), c.ld, c.sb, c.L + at(w0, 0), c.ld, c.sb,
+                  np - w0, w0, w0, 1.0, 0.0, 0, K_LE_COL, c.batch, c.st)) != cudaSuccess) return e;
   }
-  for (int k = 0; k + 1 < nblk; k++) {
-    const int rows1 = np - (k + 1) * NB;            // rows below block row k
-    // (a) rank-NB update of block column k+1
+  while (c0 + w0 < np) {
+    // panel [c0, c1) is factored and solved; the next one is [c1, c2)
+    const int c1 = c0 + w0, w1 = std::min(pw.at(c1), np - c1), c2 = c1 + w1;
+    const int rows1 = np - c1;                      // rows below panel [c0, c1)
+    // (a) rank-w0 update of block column [c1, c2)
     bool chain_released = false;
     g_trace_label = "a:colupd";
     if (!lookahead) {
-      // batched problems (no panel chain to protect): the NB x NB diagonal block of the column is symmetric - lower
+      // batched problems (no panel chain to protect): the diagonal block of the column is symmetric - lower
       // tiles only, and only the lower fragments of its diagonal tiles - then the rectangle below it
-      if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1), c.ld,
-                    c.sb, NB, NB, NB, -1.0, 1.0, 1, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
-      if (rows1 > NB &&
-          (e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 2, k + 1), c.ld,
-                    c.sb, rows1 - NB, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+      if ((e = gemm(true, true, c.L + at(c1, c0), c.ld, c.sb, c.L + at(c1, c0), c.ld, c.sb, c.A + at(c1, c1), c.ld,
+                    c.sb, w1, w1, w0, -1.0, 1.0, 1, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+      if (rows1 > w1 &&
+          (e = gemm(true, true, c.L + at(c2, c0), c.ld, c.sb, c.L + at(c1, c0), c.ld, c.sb, c.A + at(c2, c1), c.ld,
+                    c.sb, rows1 - w1, w1, w0, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
     } else {
       // look-ahead: the diagonal block of the column first - it is all the panel chain needs - then the rows below it,
       // which only the TRSM of the panel needs.  FFGP_SPLIT_COLUPD=1 enables it; measured at N = 8192: 20.9-21.6 ms/eval
       // against 20.6 with the single launch (the chain is not what bounds a step, profiles/r01_c2_schedule_experiments.txt)
-      const int rows_first = (aux && split_colupd() && rows1 > NB) ? NB : rows1;
-      if ((e = gemm(true, true, c.L + at(k + 1, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 1, k + 1),
-                    c.ld, c.sb, rows_first, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+      const int rows_first = (aux && split_colupd() && rows1 > w1) ? w1 : rows1;
+      if ((e = gemm(true, true, c.L + at(c1, c0), c.ld, c.sb, c.L + at(c1, c0), c.ld, c.sb, c.A + at(c1, c1),
+                    c.ld, c.sb, rows_first, w1, w0, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
       if (rows_first < rows1) {
         if ((e = cudaEventRecord(aux->ev_main, c.st)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(aux->st, aux->ev_main, 0)) != cudaSuccess) return e;
         chain_released = true;
-        if ((e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 1, k), c.ld, c.sb, c.A + at(k + 2, k + 1),
-                      c.ld, c.sb, rows1 - NB, NB, NB, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
+        if ((e = gemm(true, true, c.L + at(c2, c0), c.ld, c.sb, c.L + at(c1, c0), c.ld, c.sb, c.A + at(c2, c1),
+                      c.ld, c.sb, rows1 - w1, w1, w0, -1.0, 1.0, 0, K_FULL, c.batch, c.st)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(aux->ev_rest, c.st)) != cudaSuccess) return e;
       }
     }
@@ -491,10 +518,10 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
       }
       ps = aux->st;
     }
-    // (b) panel k+1: diagonal block (factor + inverse), then TRSM of the rows below it
+    // (b) panel [c1, c2): diagonal block (factor + inverse), then TRSM of the rows below it
     g_trace_label = "b:panel";
-    if ((e = factor_rec(aux ? ca : c, (k + 1) * NB, NB)) != cudaSuccess) return e;
-    const int rows2 = np - (k + 2) * NB;
+    if ((e = factor_rec(aux ? ca : c, c1, w1)) != cudaSuccess) return e;
+    const int rows2 = np - c2;
     // Schedule 2 (FFGP_SCHED=2, experiment): the trailing update runs as a persistent grid that leaves FFGP_SYRK_RESERVE
     // SMs to the diagonal-block chain on the side stream, and the TRSM of the panel follows it on the MAIN stream (all
     // SMs).  The chain shrinks from ~200 to ~140 us per block but a step is bound by SYRK + TRSM + column update:
@@ -504,15 +531,15 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
       if (!sched2) {
         g_trace_label = "b:trsm";
         if (chain_released && (e = cudaStreamWaitEvent(ps, aux->ev_rest, 0)) != cudaSuccess) return e;
-        if ((e = gemm(true, true, c.A + at(k + 2, k + 1), c.ld, c.sb, c.M + at(k + 1, k + 1), c.ld, c.sb,
-                      c.L + at(k + 2, k + 1), c.ld, c.sb, rows2, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, ps)) != cudaSuccess)
+        if ((e = gemm(true, true, c.A + at(c2, c1), c.ld, c.sb, c.M + at(c1, c1), c.ld, c.sb,
+                      c.L + at(c2, c1), c.ld, c.sb, rows2, w1, w1, 1.0, 0.0, 0, K_LE_COL, c.batch, ps)) != cudaSuccess)
           return e;
       }
-      // (c) rest of the trailing update of step k (independent of the panel): lower tiles of A[k+2:, k+2:]
+      // (c) rest of the trailing update with panel [c0, c1) (independent of the new panel): lower tiles of A[c2:, c2:]
       g_trace_label = "c:syrk";
       if (aux) g_reserve_sms = syrk_reserve();
-      e = gemm(true, true, c.L + at(k + 2, k), c.ld, c.sb, c.L + at(k + 2, k), c.ld, c.sb, c.A + at(k + 2, k + 2), c.ld,
-               c.sb, rows2, rows2, NB, -1.0, 1.0, 1, K_FULL, c.batch, c.st);
+      e = gemm(true, true, c.L + at(c2, c0), c.ld, c.sb, c.L + at(c2, c0), c.ld, c.sb, c.A + at(c2, c2), c.ld,
+               c.sb, rows2, rows2, w0, -1.0, 1.0, 1, K_FULL, c.batch, c.st);
       g_reserve_sms = 0;
       if (e != cudaSuccess) return e;
     }
@@ -522,16 +549,17 @@ static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahea
     }
     if (sched2 && rows2 > 0) {
       g_trace_label = "b:trsm";
-      if ((e = gemm(true, true, c.A + at(k + 2, k + 1), c.ld, c.sb, c.M + at(k + 1, k + 1), c.ld, c.sb,
-                    c.L + at(k + 2, k + 1), c.ld, c.sb, rows2, NB, NB, 1.0, 0.0, 0, K_LE_COL, c.batch, c.st)) != cudaSuccess)
+      if ((e = gemm(true, true, c.A + at(c2, c1), c.ld, c.sb, c.M + at(c1, c1), c.ld, c.sb,
+                    c.L + at(c2, c1), c.ld, c.sb, rows2, w1, w1, 1.0, 0.0, 0, K_LE_COL, c.batch, c.st)) != cudaSuccess)
         return e;
     }
-    if ((k + 2) * 2 == nblk && (e = at_half()) != cudaSuccess) return e;
+    if ((e = at_cols(c2)) != cudaSuccess) return e;
+    c0 = c1; w0 = w1;
   }
   return cudaSuccess;
 }
 static cudaError_t potrf_right_looking(const FactorCtx& c, int np, bool lookahead) {
-  return potrf_right_looking(c, np, lookahead, []() { return cudaSuccess; });
+  return potrf_right_looking(c, np, lookahead, [](int) { return cudaSuccess; });
 }
 
 // M21 = -M22 L21 M11 for the node [off, off+n) split at h (general, sequential; used when np/NB is not a power of 2)
@@ -549,8 +577,8 @@ static cudaError_t trtri_rec(const FactorCtx& c, int off, int n, int NB) {
               K_GE_COL, c.batch, c.st);
 }
 
-static cudaError_t trtri_bottom_up(const FactorCtx& c, int np) {
-  int NB = outer_nb();
+static cudaError_t trtri_bottom_up(const FactorCtx& c, int np, int nb0 = 0) {
+  int NB = nb0 > 0 ? nb0 : outer_nb();      // nb0: width of the diagonal blocks whose inverses are already complete
   if (np % NB != 0) NB = BASE_N;
   const int nblk = np / NB;
   if (nblk & (nblk - 1)) return trtri_rec(c, 0, np, NB);      // not a power of two: plain recursion
@@ -569,11 +597,11 @@ static cudaError_t trtri_bottom_up(const FactorCtx& c, int np) {
   return cudaSuccess;
 }
 
-static cudaError_t trtri_bottom_up_range(const FactorCtx& c, int off, int n) {
+static cudaError_t trtri_bottom_up_range(const FactorCtx& c, int off, int n, int nb0 = 0) {
   FactorCtx r = c;
   const long long d = (long long)off * c.ld + off;
   r.A += d; r.L += d; r.M += d;
-  return trtri_bottom_up(r, n);
+  return trtri_bottom_up(r, n, nb0);
 }
 
 // Single large problem: factorisation AND triangular inverse with the first half of the inverse overlapped with the
@@ -590,6 +618,14 @@ static int bg_cta_cap() {
   return v;
 }
 
+// FFGP_BG_RESERVE = R > 0: the background products run as persistent grids on all SMs but R, which stay free for the
+// panel chain and the trailing updates of the chain-bound steps (a 128 x 128 TMA GEMM CTA owns its SM until its tile retires)
+static int bg_reserve() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFGP_BG_RESERVE"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int stop_after, bool* done) {
   *done = false;
   int NB = outer_nb();
@@ -602,54 +638,76 @@ static cudaError_t factor_and_invert_overlapped(const FactorCtx& c, int np, int 
   cudaError_t e;
   AuxStream* aux = nullptr;
   if ((e = get_aux(&aux)) != cudaSuccess) return e;
-  const int h = np / 2;
-  const long long o21 = (long long)h * c.ld, o22 = (long long)h * c.ld + h;
   // fork: the factorisation runs on the library's middle-priority stream
   if ((e = cudaEventRecord(aux->ev_fork, c.st)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(aux->st_bulk, aux->ev_fork, 0)) != cudaSuccess) return e;
   FactorCtx cb = c; cb.st = aux->st_bulk;
   FactorCtx cg = c; cg.st = aux->st_bg;
-  auto at_half = [&]() -> cudaError_t {
-    if (stop_after == 1) return cudaSuccess;
+  // Row-progressive inverse.  Hook points q = np/2, 3np/4, 7np/8, .. (FFGP_HOOKS of them, default 3): when the block
+  // columns [0, q) of L are final, the rows [p, q) of M (p = the previous hook point) can be completed in the
+  // background, and the part of the remaining rows' inverse that only needs L[:, 0:q) accumulated into X (kept in the
+  // dead strictly-lower part of A):
+  //   1. M[p:q, p:q]  bottom-up from the diagonal-block inverses
+  //   2. M[p:q, 0:p]  = -M[p:q, p:q] X[p:q, 0:p]                                  (p > 0)
+  //   3. X[q:np, 0:q] = L[q:np, 0:q] M[0:q, 0:q], in column chunks of KC: the chunk's own triangular block first
+  //      (first touch), then its full-depth contribution to the columns on its left (beta = 1)
+  // After the factorisation: M[p:np, p:np] bottom-up, M[p:np, 0:p] = -M[p:np, p:np] X[p:np, 0:p] for the last hook point p.
+  // With the single hook at np/2 this is the round-1 schedule (X = W = L21 M11); the later hooks move ~1.7 ms of
+  // products from the tail into the chain-bound last quarter of the factorisation, where most SMs idle.
+  static int nhooks = -1;
+  if (nhooks < 0) { const char* ev = getenv("FFGP_HOOKS"); nhooks = ev ? atoi(ev) : 3; if (nhooks < 1) nhooks = 1; }
+  static int KCv = -1;                             // FFGP_BG_KC: K chunk of the background X products (256 / 512 / 1024)
+  if (KCv < 0) { const char* ev = getenv("FFGP_BG_KC"); KCv = ev ? atoi(ev) : 512; if (KCv < 128 || KCv % 128) KCv = 512; }
+  const int nb0 = panel_widths(np, NB, true).min_width();   // narrowest panel of the sweep: where the bottom-up inverse starts
+  int p_done = 0;                                   // rows [0, p_done) of M are complete (or queued on the background stream)
+  int hooks_left = nhooks;
+  auto at_cols = [&](int q) -> cudaError_t {       // called when block columns [0, q) are final
+    if (stop_after == 1 || hooks_left == 0) return cudaSuccess;
+    const int rest = np - p_done;                  // next hook point: the midpoint of what is left
+    if (q != p_done + rest / 2 || (rest / 2) % NB != 0 || rest / 2 < NB) return cudaSuccess;
+    const int p = p_done;
     cudaError_t e2;
     if ((e2 = cudaEventRecord(aux->ev_half, cb.st)) != cudaSuccess) return e2;
     if ((e2 = cudaStreamWaitEvent(cg.st, aux->ev_half, 0)) != cudaSuccess) return e2;
     g_cta_cap = bg_cta_cap();
+    g_reserve_sms = bg_reserve();
     g_trace_label = "bg:trtri";
-    e2 = trtri_bottom_up_range(cg, 0, h);
-    // W = L21 M11 -> A21 (dead: every block column of the leading half has been solved)
-    // W = L21 M11 -> A21 (dead: every block column of the leading half has been solved), in K chunks of 512 with
-    // beta = 1 accumulation: one launch with K up to h keeps every SM busy for ~100 us per tile and stalled the panel
-    // chain by 1.7 ms (profiles/r01_timeline_c2_v1.txt, steps 19-20); with 512-deep tiles an SM frees up every ~7 us.
+    e2 = trtri_bottom_up_range(cg, p, q - p, nb0);
+    if (p > 0 && e2 == cudaSuccess)
+      e2 = gemm(true, false, c.M + (long long)p * c.ld + p, c.ld, c.sb, c.A + (long long)p * c.ld, c.ld, c.sb,
+                c.M + (long long)p * c.ld, c.ld, c.sb, q - p, p, q - p, -1.0, 0.0, 0, K_LE_ROW, c.batch, cg.st);
+    // one launch with K up to np/2 keeps every SM busy for ~100 us per tile and stalled the panel chain by 1.7 ms
+    // (profiles/r01_timeline_c2_v1.txt, steps 19-20); with 512-deep tiles an SM frees up every ~7 us.
     g_trace_label = "bg:W";
-    static int KCv = -1;                             // FFGP_BG_KC: K chunk of the background W product (256 / 512 / 1024)
-    if (KCv < 0) { const char* ev = getenv("FFGP_BG_KC"); KCv = ev ? atoi(ev) : 512; if (KCv < 128 || KCv % 128) KCv = 512; }
-    const int KC = KCv;
-    for (int s0 = 0; s0 < h && e2 == cudaSuccess; s0 += KC) {
-      const int kc = std::min(KC, h - s0);
-      // columns [s0, s0 + kc): first touch, the chunk's own lower-triangular block of M11 (K range starts at the column)
-      e2 = gemm(true, false, c.L + o21 + s0, c.ld, c.sb, c.M + (long long)s0 * c.ld + s0, c.ld, c.sb, c.A + o21 + s0, c.ld, c.sb,
-                h, kc, kc, 1.0, 0.0, 0, K_GE_COL, c.batch, cg.st);
-      // columns [0, s0): accumulate this chunk's full-depth contribution
+    const long long oq = (long long)q * c.ld;      // row q of the arrays
+    for (int s0 = p; s0 < q && e2 == cudaSuccess; s0 += KCv) {
+      const int kc = std::min(KCv, q - s0);
+      e2 = gemm(true, false, c.L + oq + s0, c.ld, c.sb, c.M + (long long)s0 * c.ld + s0, c.ld, c.sb, c.A + oq + s0, c.ld, c.sb,
+                np - q, kc, kc, 1.0, 0.0, 0, K_GE_COL, c.batch, cg.st);
       if (s0 > 0 && e2 == cudaSuccess)
-        e2 = gemm(true, false, c.L + o21 + s0, c.ld, c.sb, c.M + (long long)s0 * c.ld, c.ld, c.sb, c.A + o21, c.ld, c.sb, h, s0,
+        e2 = gemm(true, false, c.L + oq + s0, c.ld, c.sb, c.M + (long long)s0 * c.ld, c.ld, c.sb, c.A + oq, c.ld, c.sb, np - q, s0,
                   kc, 1.0, 1.0, 0, K_FULL, c.batch, cg.st);
     }
     g_cta_cap = 0;
+    g_reserve_sms = 0;
+    p_done = q;
+    --hooks_left;
     return e2;
   };
-  if ((e = potrf_right_looking(cb, np, true, at_half)) != cudaSuccess) return e;
+  if ((e = potrf_right_looking(cb, np, true, at_cols)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(aux->ev_join, cb.st)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(c.st, aux->ev_join, 0)) != cudaSuccess) return e;
   *done = true;
   if (stop_after == 1) return cudaSuccess;
-  // inverse of the trailing half, then the one product that needs both halves
+  if (p_done == 0) { *done = false; return cudaErrorUnknown; }   // cannot happen: nblk >= 8 is a power of two
+  // inverse of the trailing rows, then the one product that needs both parts
   g_trace_label = "post:trtri";
-  if ((e = trtri_bottom_up_range(c, h, h)) != cudaSuccess) return e;
+  const int p = p_done;
+  if ((e = trtri_bottom_up_range(c, p, np - p, nb0)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(aux->ev_bg, cg.st)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(c.st, aux->ev_bg, 0)) != cudaSuccess) return e;
-  return gemm(true, false, c.M + o22, c.ld, c.sb, c.A + o21, c.ld, c.sb, c.M + o21, c.ld, c.sb, h, h, h, -1.0, 0.0, 0, K_LE_ROW,
-              c.batch, c.st);
+  return gemm(true, false, c.M + (long long)p * c.ld + p, c.ld, c.sb, c.A + (long long)p * c.ld, c.ld, c.sb,
+              c.M + (long long)p * c.ld, c.ld, c.sb, np - p, p, np - p, -1.0, 0.0, 0, K_LE_ROW, c.batch, c.st);
 }
 
 // FFGP_DEBUG_STOP_AFTER=1|2|3 truncates an evaluation after potrf | trtri | the S = M^T M product (results are then
@@ -733,7 +791,7 @@ static int assemble_and_factor(const DenseArgs& a, const DenseWs& w, int b0, int
   }
   FFGP_CUDA(potrf_right_looking(c, w.np, /*lookahead=*/nb < 8));
   if (debug_stop_after() == 1) return 0;              // tools/phase_times.py: time the phases separately
-  FFGP_CUDA(trtri_bottom_up(c, w.np));
+  FFGP_CUDA(trtri_bottom_up(c, w.np, nb < 8 ? panel_widths(w.np, outer_nb(), true).min_width() : 0));
   return 0;
 }
 
