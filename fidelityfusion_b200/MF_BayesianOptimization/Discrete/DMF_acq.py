@@ -10,7 +10,7 @@ from ... import _lib as B
 from ... import ops
 
 PI = 3.1415926
-KINDS = {'UCB': 0, 'EI': 1, 'PI': 2}
+KINDS = {'UCB': 0, 'EI': 1, 'PI': 2, 'UCB_STD': 3, 'PI_CDF': 4}       # 3 / 4: Bayesian_optimization/acq.py's UCB / PI
 
 
 class _Acq(torch.autograd.Function):
@@ -141,7 +141,7 @@ def batched_candidate_scores(x, y, length_scales, signal_variance, log_beta, xs,
     """BASELINE config 5 as its real consumer uses it: B independent candidate GPs (v1/CFKG.py:124-129 re-fits one GP
     per candidate), each scored at its own test points, nothing leaves the device.  Returns scores [B, N*]."""
     from ...batched import batched_cigp_eval
-    out = batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs, want_grad=False)
-    mean = out['mean'][..., 0] if out['mean'].dim() == 3 else out['mean']
-    with torch.no_grad():
-        return acquisition(mean, out['var'], kind, f_best=f_best, beta=beta, xi=xi)
+    # the score is written by the epilogue of the sweep (ffgp_batched_pack_acq_f64): no launch of its own
+    out = batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs, want_grad=False,
+                            acq=dict(kind=KINDS[kind] if isinstance(kind, str) else kind, f_best=f_best, beta=beta, xi=xi))
+    return out['score']

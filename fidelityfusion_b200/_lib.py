@@ -59,6 +59,8 @@ def lib():
     _sig(L.ffgp_adam_step_f64, i, [vp, vp, i] + [ctypes.c_double] * 4 + [i, vp, vp, i, vp])
     _sig(L.ffgp_row_match_f64, i, [vp, vp, i, i, i, vp, vp])
     _sig(L.ffgp_batched_pack_f64, i, [vp] * 10 + [i] * 7 + [ctypes.c_double, ctypes.c_double, vp, i, vp])
+    _sig(L.ffgp_batched_pack_acq_f64, i, [vp] * 10 + [i] * 7 + [ctypes.c_double, ctypes.c_double, i] + [ctypes.c_double] * 3 +
+         [i, vp, i, vp])
     _sig(L.ffgp_potrf_trtri_f64, i, [vp, i, i, vp, sz, vp, vp, vp, vp, vp])
     _sig(L.ffgp_mode_dot_f64, i, [vp, vp, vp, ll, i, ll, i, i, vp])
     _sig(L.ffgp_mode_gram_scratch_bytes, sz, [ll, ll, i, i])

@@ -23,7 +23,10 @@ PI = 3.1415
 EPS = 1e-9
 
 
-def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True, check=True):
+ACQ_KINDS = {'UCB_MF': 0, 'EI': 1, 'PI_MF': 2, 'UCB': 3, 'PI': 4}
+
+
+def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True, check=True, acq=None):
     """x [B,n,d], y [B,n,D], length_scales [B,d], signal_variance [B], log_beta [B] (raw reference parameters),
     xs [B,ns,d] or None.  Returns dict: nll [B] (= -cigp.negative_log_likelihood), g_length_scales [B,d],
     g_signal_variance [B], g_log_beta [B], and mean [B,ns,D], var [B,ns] (diag of cigp.forward's covariance).
@@ -34,7 +37,11 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     check=True raises torch.linalg.LinAlgError at the call when a covariance is not positive definite, like the
     reference's torch.linalg.cholesky - which costs a host synchronisation per call.  check=False keeps the call
     asynchronous (sweeps can be enqueued back to back) and returns the LAPACK-style status as out['info'] (fp64 [B],
-    0 = ok, k = leading minor k not PD) for the caller to inspect, e.g. once per optimisation step: `check_batch_info`."""
+    0 = ok, k = leading minor k not PD) for the caller to inspect, e.g. once per optimisation step: `check_batch_info`.
+
+    acq = dict(kind='EI' | 'UCB' | 'PI' | 'UCB_MF' | 'PI_MF', f_best=, beta=, xi=, round_f32=True) (needs xs, D = 1) adds
+    out['score'] [B,ns]: the acquisition score of every test point, computed in the epilogue that writes the result rows
+    (ffgp_batched_pack_acq_f64) - no extra launch, and it travels through sharded_cigp_eval's single all-gather."""
     from . import _lib as B
     L = B.lib()
     Bn, n, d = x.shape
@@ -43,7 +50,7 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     if not x.is_cuda:
         raise B.FFGPError('fidelityfusion_b200 operates on CUDA tensors only (no CPU fallback)')
     if Bn == 0:
-        return empty_result(d, D, 0 if xs is None else xs.shape[1], want_grad, check, dev)
+        return empty_result(d, D, 0 if xs is None else xs.shape[1], want_grad, check, dev, acq is not None)
     f64 = lambda t: t.detach().to(torch.float64).contiguous()
     xc, yc = f64(x), f64(y)
     ls, sv, lb = f64(length_scales), f64(signal_variance).reshape(Bn), f64(log_beta).reshape(Bn)
@@ -75,20 +82,27 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     # ONE launch writes the packed result rows: NLL constant, chain rule to the raw parameters, predictions and (for the
     # asynchronous mode) the status column.  The dict entries below are views of that buffer; sharded_cigp_eval ships
     # the buffer itself through its single all-gather.
-    keys, widths = result_layout(d, D, ns, want_grad, check)
+    if acq is not None and (ns == 0 or D != 1):
+        raise ValueError('acq needs test points xs and a single output column (D = 1)')
+    keys, widths = result_layout(d, D, ns, want_grad, check, acq is not None)
     ld = sum(widths)
     packed = torch.empty(Bn, ld, dtype=torch.float64, device=dev)
-    rc = L.ffgp_batched_pack_f64(B.ptr(nll), B.ptr(g_il), B.ptr(g_amp), B.ptr(g_diag), B.ptr(mean), B.ptr(var), B.ptr(info),
-                                 B.ptr(ls), B.ptr(sv), B.ptr(lb), Bn, n, d, D, ns, int(want_grad), int(not check),
-                                 0.5 * n * D * math.log(2 * PI), EPS, B.ptr(packed), ld, B.stream_ptr())
-    B.check(rc, 'ffgp_batched_pack_f64')
+    a = acq or {}
+    kind = a.get('kind', 'EI')
+    rc = L.ffgp_batched_pack_acq_f64(B.ptr(nll), B.ptr(g_il), B.ptr(g_amp), B.ptr(g_diag), B.ptr(mean), B.ptr(var), B.ptr(info),
+                                     B.ptr(ls), B.ptr(sv), B.ptr(lb), Bn, n, d, D, ns, int(want_grad), int(not check),
+                                     0.5 * n * D * math.log(2 * PI), EPS,
+                                     -1 if acq is None else (ACQ_KINDS[kind] if isinstance(kind, str) else int(kind)),
+                                     float(a.get('f_best', 0.0)), float(a.get('beta', 1.0)), float(a.get('xi', 0.01)),
+                                     int(bool(a.get('round_f32', True))), B.ptr(packed), ld, B.stream_ptr())
+    B.check(rc, 'ffgp_batched_pack_acq_f64')
     out = unpack_results(packed, result_shapes(d, D, ns), keys)
     out['_packed'] = packed
     return out
 
 
-def result_layout(d, D, ns, want_grad, check):
-    """(keys, column widths) of a packed result row, in the order ffgp_batched_pack_f64 writes them."""
+def result_layout(d, D, ns, want_grad, check, with_score=False):
+    """(keys, column widths) of a packed result row, in the order ffgp_batched_pack_acq_f64 writes them."""
     keys, widths = ['nll'], [1]
     if want_grad:
         keys += ['g_length_scales', 'g_signal_variance', 'g_log_beta']
@@ -96,6 +110,9 @@ def result_layout(d, D, ns, want_grad, check):
     if ns:
         keys += ['mean', 'var']
         widths += [ns * D, ns]
+        if with_score:
+            keys.append('score')
+            widths.append(ns)
     if not check:
         keys.append('info')
         widths.append(1)
@@ -104,10 +121,10 @@ def result_layout(d, D, ns, want_grad, check):
 
 def result_shapes(d, D, ns):
     return {'nll': (), 'g_length_scales': (d,), 'g_signal_variance': (), 'g_log_beta': (), 'mean': (ns, D), 'var': (ns,),
-            'info': ()}
+            'score': (ns,), 'info': ()}
 
 
-def empty_result(d, D, ns, want_grad, check, device):
+def empty_result(d, D, ns, want_grad, check, device, with_score=False):
     """The result dict of a batch of ZERO problems (a rank whose block is empty when there are fewer problems than
     ranks): nothing to compute, but the rank still joins the collective with correctly shaped fields."""
     z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=device)
@@ -118,6 +135,8 @@ def empty_result(d, D, ns, want_grad, check, device):
         out.update(g_length_scales=z(0, d), g_signal_variance=z(0), g_log_beta=z(0))
     if ns:
         out.update(mean=z(0, ns, D), var=z(0, ns))
+        if with_score:
+            out['score'] = z(0, ns)
     return out
 
 
@@ -149,12 +168,14 @@ def unpack_results(buf, shapes, keys):
 
 
 def sharded_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True, group=None,
-                      compute_fn=batched_cigp_eval, check=True):
+                      compute_fn=batched_cigp_eval, check=True, acq=None):
     """Every rank passes the FULL problem set (or at least its own block - only [lo,hi) is read) and receives the
     full result set.  Falls back to a single-rank call when torch.distributed is not initialised.
     `compute_fn` exists so the CPU (gloo) tests can exercise the partition/gather logic without a GPU."""
     import torch.distributed as dist
     kw = {} if check else {'check': False}
+    if acq is not None:
+        kw['acq'] = acq
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return compute_fn(x, y, length_scales, signal_variance, log_beta, xs, want_grad, **kw)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -165,8 +186,8 @@ def sharded_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
         res = compute_fn(x[sl], y[sl], length_scales[sl], signal_variance[sl], log_beta[sl],
                          None if xs is None else xs[sl], want_grad, **kw)
     else:           # fewer problems than ranks: skip the compute, still join the collective (the others would hang)
-        res = empty_result(x.shape[2], y.shape[2], 0 if xs is None else xs.shape[1], want_grad, check, x.device)
-    keys = [k for k in ('nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var', 'info') if k in res]
+        res = empty_result(x.shape[2], y.shape[2], 0 if xs is None else xs.shape[1], want_grad, check, x.device, acq is not None)
+    keys = [k for k in ('nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var', 'score', 'info') if k in res]
     shapes = {k: tuple(res[k].shape[1:]) for k in keys}
     local = res['_packed'] if '_packed' in res else pack_results(res, keys)      # the CUDA path packs in its own kernel
     counts = [shard_range(Bn, r, world) for r in range(world)]

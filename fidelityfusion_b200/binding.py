@@ -51,6 +51,7 @@ DATA_ALIASES = {
 ACQ_ALIASES = {
     'MF_BayesianOptimization.Discrete.DMF_acq':
         (_P + 'MF_BayesianOptimization.Discrete.DMF_acq', 'MF_BayesianOptimization/Discrete/DMF_acq.py'),
+    'Bayesian_optimization.acq': (_P + 'Bayesian_optimization.acq', 'Bayesian_optimization/acq.py'),
 }
 
 _installed = {}

@@ -1265,14 +1265,23 @@ int ffgp_dense_predict_bwd_f64(const double* x, const double* xs, const double* 
   return 0;
 }
 
+static AcqConsts acq_consts(int kind, double f_best, double beta, double xi, int round_f32) {
+  AcqConsts c;
+  c.kind = kind; c.f_best = f_best; c.beta = beta; c.xi = xi;
+  c.std_min = 1e-9; c.two_pi = 2.0 * 3.1415926;          /* DMF_acq.py:7,98,121; acq.py:178,226 */
+  c.round_f32 = round_f32;
+  return c;
+}
+
 int ffgp_acquisition_f64(const double* mean, const double* var, int m, int kind, double f_best, double beta, double xi,
                          int round_f32, double* score, double* d_mean, double* d_var, void* stream) {
   if (!mean || !var || !score) return fail(-1, "ffgp_acquisition_f64: null pointer");
-  if (m <= 0 || kind < 0 || kind > 2) return fail(-2, "ffgp_acquisition_f64: bad size or kind (0 UCB, 1 EI, 2 PI)");
+  if (m <= 0 || kind < 0 || kind > 4)
+    return fail(-2, "ffgp_acquisition_f64: bad size or kind (0 UCB_MF, 1 EI, 2 PI_MF, 3 UCB on the std, 4 PI as cdf)");
   AcqParams p;
-  p.mean = mean; p.var = var; p.m = m; p.kind = kind; p.f_best = f_best; p.beta = beta; p.xi = xi;
-  p.std_min = 1e-9; p.two_pi = 2.0 * 3.1415926;          /* DMF_acq.py:7,98,121 */
-  p.round_f32 = round_f32; p.score = score; p.d_mean = d_mean; p.d_var = d_var;
+  p.mean = mean; p.var = var; p.m = m;
+  p.c = acq_consts(kind, f_best, beta, xi, round_f32);
+  p.score = score; p.d_mean = d_mean; p.d_var = d_var;
   acq_kernel<<<(m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
   FFGP_LAUNCHED();
   return 0;
@@ -1291,26 +1300,39 @@ int ffgp_adam_step_f64(void* const* table, const int* sizes, int ntensors, doubl
   return 0;
 }
 
-int ffgp_batched_pack_f64(const double* nll_core, const double* g_inv_ls, const double* g_amp, const double* g_diag,
-                          const double* mean, const double* var, const int* info, const double* length_scales,
-                          const double* signal_variance, const double* log_beta, int batch, int n, int d, int D, int ns,
-                          int want_grad, int with_info, double nll_const, double eps, double* out, int ld_out, void* stream) {
+int ffgp_batched_pack_acq_f64(const double* nll_core, const double* g_inv_ls, const double* g_amp, const double* g_diag,
+                              const double* mean, const double* var, const int* info, const double* length_scales,
+                              const double* signal_variance, const double* log_beta, int batch, int n, int d, int D, int ns,
+                              int want_grad, int with_info, double nll_const, double eps, int acq_kind, double f_best,
+                              double beta, double xi, int round_f32, double* out, int ld_out, void* stream) {
   if (!nll_core || !out) return fail(-1, "ffgp_batched_pack_f64: null pointer");
   if (want_grad && (!g_inv_ls || !g_amp || !g_diag || !length_scales || !signal_variance || !log_beta))
     return fail(-1, "ffgp_batched_pack_f64: gradient inputs missing");
   if (ns > 0 && (!mean || !var)) return fail(-1, "ffgp_batched_pack_f64: prediction inputs missing");
   if (with_info && !info) return fail(-1, "ffgp_batched_pack_f64: info missing");
   if (batch <= 0 || n <= 0 || d < 0 || D <= 0 || ns < 0) return fail(-2, "ffgp_batched_pack_f64: bad size");
-  const int need = 1 + (want_grad ? d + 2 : 0) + (ns > 0 ? ns * D + ns : 0) + (with_info ? 1 : 0);
+  if (acq_kind > 4) return fail(-2, "ffgp_batched_pack_acq_f64: bad acquisition kind");
+  if (acq_kind >= 0 && (ns <= 0 || D != 1)) return fail(-2, "ffgp_batched_pack_acq_f64: scores need test points and D = 1");
+  const int need = 1 + (want_grad ? d + 2 : 0) + (ns > 0 ? ns * D + ns : 0) + (acq_kind >= 0 ? ns : 0) + (with_info ? 1 : 0);
   if (ld_out < need) return fail(-2, "ffgp_batched_pack_f64: ld_out too small");
   PackParams p;
   p.nll_core = nll_core; p.g_il = g_inv_ls; p.g_amp = g_amp; p.g_diag = g_diag; p.mean = mean; p.var = var; p.info = info;
   p.ls = length_scales; p.sv = signal_variance; p.lb = log_beta;
   p.B = batch; p.n = n; p.d = d; p.D = D; p.ns = ns; p.want_grad = want_grad; p.with_info = with_info;
   p.nll_const = nll_const; p.eps = eps; p.out = out; p.ld = ld_out;
+  p.acq = acq_consts(acq_kind < 0 ? -1 : acq_kind, f_best, beta, xi, round_f32);
   pack_results_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(p);
   FFGP_LAUNCHED();
   return 0;
+}
+
+int ffgp_batched_pack_f64(const double* nll_core, const double* g_inv_ls, const double* g_amp, const double* g_diag,
+                          const double* mean, const double* var, const int* info, const double* length_scales,
+                          const double* signal_variance, const double* log_beta, int batch, int n, int d, int D, int ns,
+                          int want_grad, int with_info, double nll_const, double eps, double* out, int ld_out, void* stream) {
+  return ffgp_batched_pack_acq_f64(nll_core, g_inv_ls, g_amp, g_diag, mean, var, info, length_scales, signal_variance, log_beta,
+                                   batch, n, d, D, ns, want_grad, with_info, nll_const, eps, -1, 0.0, 0.0, 0.0, 0, out, ld_out,
+                                   stream);
 }
 
 int ffgp_row_match_f64(const double* a, const double* b, int na, int nb, int d, int* match, void* stream) {

@@ -4,8 +4,12 @@
 // [nll | g_length_scales[d] | g_signal_variance | g_log_beta | mean[ns*D] | var[ns] | info] that the multi-GPU
 // all-gather ships.  Replaces ~15 elementwise / cat launches per sweep (part of the 7 % that
 // separated 7.44x from 8x at 8 GPUs).  One CTA per problem; fixed-order reduction of the diagonal gradient.
+// With acq.kind >= 0 the row also carries the acquisition score of every test point (the erfc / exp
+// epilogue of the batched posterior - the candidates' scores leave the sweep in the same row, and through the same
+// all-gather, as the predictions they are computed from): [.. | mean[ns] | var[ns] | score[ns] | info], D = 1.
 #pragma once
 #include <cuda_runtime.h>
+#include "acq_kernels.cuh"
 
 namespace ffgp {
 
@@ -16,6 +20,7 @@ struct PackParams {
   int B, n, d, D, ns, want_grad, with_info;
   double nll_const, eps;
   double* out; int ld;                                            // [B][ld]
+  AcqConsts acq;                                                  // kind < 0: no score block
 };
 
 __global__ void __launch_bounds__(128) pack_results_kernel(const PackParams p) {
@@ -48,6 +53,14 @@ __global__ void __launch_bounds__(128) pack_results_kernel(const PackParams p) {
     for (int k = tid; k < nm; k += 128) o[c + k] = p.mean[(long long)b * nm + k];
     for (int k = tid; k < p.ns; k += 128) o[c + nm + k] = p.var[(long long)b * p.ns + k];
     c += nm + p.ns;
+    if (p.acq.kind >= 0) {                                        // D == 1 (checked by the entry point)
+      for (int k = tid; k < p.ns; k += 128) {
+        double s, dm, dv;
+        acq_score(p.acq, p.mean[(long long)b * p.ns + k], p.var[(long long)b * p.ns + k], s, dm, dv);
+        o[c + k] = s;
+      }
+      c += p.ns;
+    }
   }
   if (p.with_info && tid == 0) o[c] = (double)p.info[b];
 }

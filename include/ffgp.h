@@ -151,6 +151,8 @@ int ffgp_dense_predict_bwd_f64(const double* x, const double* xs, const double* 
  * whose EI goes through scipy.stats.norm on the host (DMF_acq.py:104).
  *   kind 0: mean + beta * var            kind 1: t Phi(z) + s phi(z), t = mean - f_best - xi, s = max(sqrt(var), 1e-9), z = t / s
  *   kind 2: -z^2/2 - log sqrt(2 * 3.1415926)
+ * and the single-fidelity classes of Bayesian_optimization/acq.py (UCB :135-149, PI :211-231; its EI :176-181 is kind 1):
+ *   kind 3: mean + beta * sqrt(var)      kind 4: Phi(z) (float32-rounded when round_f32; a constant: both partials are 0)
  * round_f32 != 0 (EI): Phi and phi are rounded to float32 as the reference's torch.tensor(norm.cdf(..), dtype=float32).
  * --------------------------------------------------------------------------------------- */
 int ffgp_acquisition_f64(const double* mean, const double* var, int m, int kind, double f_best, double beta, double xi,
@@ -183,6 +185,18 @@ int ffgp_batched_pack_f64(const double* nll_core, const double* g_inv_ls, const 
                           const double* mean, const double* var, const int* info, const double* length_scales,
                           const double* signal_variance, const double* log_beta, int batch, int n, int d, int D, int ns,
                           int want_grad, int with_info, double nll_const, double eps, double* out, int ld_out, void* stream);
+
+/* The same row with the acquisition score of every test point appended after the variances (D = 1, ns > 0):
+ *   [.. | mean[ns] | var[ns] | score[ns] | info],  score = ffgp_acquisition_f64's (acq_kind, f_best, beta, xi, round_f32).
+ * The erfc / exp epilogue of the batched posterior: the candidates' scores of an acquisition sweep
+ * (MF_BayesianOptimization/Discrete/DMF_acq.py:82-104, Bayesian_optimization/acq.py:118-256) leave the device-side sweep in
+ * the same row - and through the same all-gather - as the predictions; the reference round-trips mean and variance through
+ * scipy.stats.norm on the host per candidate set (DMF_acq.py:104).  acq_kind < 0: exactly ffgp_batched_pack_f64. */
+int ffgp_batched_pack_acq_f64(const double* nll_core, const double* g_inv_ls, const double* g_amp, const double* g_diag,
+                              const double* mean, const double* var, const int* info, const double* length_scales,
+                              const double* signal_variance, const double* log_beta, int batch, int n, int d, int D, int ns,
+                              int want_grad, int with_info, double nll_const, double eps, int acq_kind, double f_best,
+                              double beta, double xi, int round_f32, double* out, int ld_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Subset / overlap matching of two fidelities' inputs: match[i] = smallest j with b[j][:] == a[i][:]

@@ -371,6 +371,26 @@ def acq_score(mean, var, kind, f_best=0.0, x_dimension=5):
     return -torch.pow(Z, 2) * 0.5 - torch.log(torch.ones(1, 1)) - torch.log(torch.sqrt(2 * PI_ACQ * torch.ones(1, 1)))
 
 
+def acq_sf_score(kind, mean, var, f_best=0.0, kappa=2.0, xi=0.01, thresholds=None):
+    """Single-fidelity acquisition classes UCB / EI / PI / PF (Bayesian_optimization/acq.py:135-149, 166-181, 211-231,
+    279-294), with the reference's scipy.stats.norm host round trip and float32 cdf / pdf tensors."""
+    from scipy.stats import norm
+    if kind == 'UCB':
+        return mean + kappa * torch.sqrt(var)
+    if kind == 'PF':
+        sigma = torch.sqrt(var)
+        pf = np.ones(mean.shape[0])
+        for i in range(len(thresholds)):
+            pf *= norm.cdf(((thresholds[i] - mean[:, i]) / sigma[:, i]).detach().numpy())
+        return pf
+    std = torch.clamp(torch.sqrt(var), min=1e-9)
+    Z = (mean - f_best - xi) / std
+    if kind == 'EI':
+        return (mean - f_best - xi) * torch.tensor(norm.cdf(Z.detach().numpy()), dtype=torch.float32) \
+            + std * torch.tensor(norm.pdf(Z.detach().numpy()), dtype=torch.float32)
+    return torch.tensor(norm.cdf(Z.detach().numpy()), dtype=torch.float32)          # PI
+
+
 def dense_nll_grads_analytic_numpy(x, y, ls_raw, sv_raw, log_beta, eps=1e-9, pi=PI_REF):
     """Independent numpy cross-check (no autograd): closed-form gradient of the cigp NLL
     through Sigma^{-1}.  Used by tests to show the analytic route the CUDA path takes

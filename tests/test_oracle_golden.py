@@ -305,3 +305,23 @@ def test_acquisition_scores_pinned_on_the_reference_class(kind):
     s.sum().backward()
     assert np.array_equal(mu.grad.numpy(), g[kind + '_dmean'])
     assert np.array_equal(np.nan_to_num(v.grad.numpy(), nan=-7.0), np.nan_to_num(g[kind + '_dvar'], nan=-7.0))
+
+
+def test_single_fidelity_acquisition_scores_pinned_on_the_reference_module():
+    """O.acq_sf_score against the unmodified Bayesian_optimization/acq.py classes (UCB :135-149, EI :166-181, PI :211-231,
+    PF :279-294; golden from oracle/gen_golden_acq_sf.py): scores and autograd partials, the float32 cdf / pdf tensors of
+    EI / PI and the clamp(std, min=1e-9) region.  Same operations in the same order: bit-exact."""
+    g = load_golden('acq_sf')
+    f_best, kappa, xi = float(g['f_best']), float(g['kappa']), float(g['xi'])
+    for kind in ('UCB', 'EI'):
+        mu = T(g['mean']).requires_grad_(True)
+        v = T(g['var']).requires_grad_(True)
+        s = O.acq_sf_score(kind, mu, v, f_best=f_best, kappa=kappa, xi=xi)
+        assert np.array_equal(s.detach().numpy(), g[kind + '_score'])
+        s.sum().backward()
+        assert np.array_equal(mu.grad.numpy(), g[kind + '_dmean'])
+        assert np.array_equal(np.nan_to_num(v.grad.numpy(), nan=-7.0), np.nan_to_num(g[kind + '_dvar'], nan=-7.0))
+    pi = O.acq_sf_score('PI', T(g['mean']), T(g['var']), f_best=f_best, xi=xi)
+    assert pi.dtype == torch.float32 and np.array_equal(pi.numpy(), g['PI_score'])
+    pf = O.acq_sf_score('PF', T(g['pf_mean']), T(g['pf_var']), thresholds=list(g['pf_thresholds']))
+    assert np.array_equal(pf, g['PF_score'])
