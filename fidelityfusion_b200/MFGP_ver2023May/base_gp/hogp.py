@@ -92,9 +92,8 @@ class HOGP(torch.nn.Module):
             self.train_x = x
             self.train_y = y
         self.compute_kernel_cache()
-        if isinstance(y_var, torch.Tensor) and y_var.numel() > 1:
-            raise NotImplementedError('tensor-valued y_var is not supported by the fused Kronecker op')
-        add = float(y_var) if not isinstance(y_var, torch.Tensor) else float(y_var.item())
+        # hogp.py:176 `A = A + y_var`: a number, or a tensor broadcast against A element by element
+        add = y_var if isinstance(y_var, torch.Tensor) and y_var.numel() > 1 else float(y_var)
         val, A, g, eig = tl.kron_nll(self.train_y, self.k_result_cache, self.noise_box.get().pow(-1), add)
         self.eigen_cache = [eigen_pairs(value=lam, vector=U) for lam, U in eig]
         self.A = A

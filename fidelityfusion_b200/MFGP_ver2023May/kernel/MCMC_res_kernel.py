@@ -7,15 +7,19 @@ an SE kernel in x times a SCALAR Monte-Carlo integral over the fidelity variable
     side effect is part of the reference's behaviour).
 
 The x part is the fused kernel-matrix assembly (ffgp_kernel_matrix_f64 / the fused NLL); the scalar integral is a
-100-element torch expression whose autograd carries the gradient to `length_scale_z` and `b`.  The samples are drawn
-from the CPU generator (as the reference does when it runs where our oracle can pin it) and moved to the parameters'
-device."""
+100-element torch expression whose autograd carries the gradient to `length_scale_z` and `b`.  By default the samples
+are drawn from the CPU generator - the numbers the reference sees when it runs on the CPU, which is where the oracle and
+the golden vectors pin it - and moved to the parameters' device.  `Kernel_res.sample_generator = 'device'` draws them
+with `torch.rand(N, device=<parameters' device>)` exactly as MCMC_res_kernel.py:48-49 is written: the numbers the
+reference sees when IT runs on CUDA (a different stream of the same seed)."""
 import torch
 
 from ... import ops
 
 
 class Kernel_res(torch.nn.Module):
+    sample_generator = 'cpu'          # 'cpu' (golden-pinned default) | 'device' (as written in the reference, see above)
+
     def __init__(self, noise_exp_format, length_scale=1., scale=1., length_scale_z=1., const_item=torch.tensor(3.).sqrt()) -> None:
         super().__init__()
         # `is True` by identity: a config DICT passed positionally by kernel_utils.create_kernel selects the linear format
@@ -50,8 +54,9 @@ class Kernel_res(torch.nn.Module):
         N = 100
         dev, dt = self.b.device, self.b.dtype
         torch.manual_seed(self.seed)
-        z1 = (torch.rand(N) * (hf1 - lf1) + lf1).to(device=dev, dtype=dt)
-        z2 = (torch.rand(N) * (hf2 - lf2) + lf2).to(device=dev, dtype=dt)
+        rdev = dev if self.sample_generator == 'device' else 'cpu'
+        z1 = (torch.rand(N, device=rdev) * (hf1 - lf1) + lf1).to(device=dev, dtype=dt)
+        z2 = (torch.rand(N, device=rdev) * (hf2 - lf2) + lf2).to(device=dev, dtype=dt)
         lz = length_scale_z.view(1, -1)
         dist_z = (z1 / lz - z2 / lz) ** 2
         z_part = (-self.b * (z1 - hf1) - self.b * (z2 - hf2) - 0.5 * dist_z).exp()

@@ -243,18 +243,48 @@ def _kron_ck(lam_cat, sizes, k, tau_t, add, dev):
     return out
 
 
+def _lambda_product(eigvals, sizes, skip=-1):
+    """prod_{m != skip} lambda_m[i_m] as a broadcastable tensor (extent 1 along `skip`)."""
+    out = None
+    for m, lam in enumerate(eigvals):
+        if m == skip:
+            continue
+        shape = [1] * len(sizes)
+        shape[m] = int(sizes[m])
+        v = lam.reshape(shape)
+        out = v if out is None else out * v
+    if out is None:
+        out = torch.ones([1] * len(sizes), dtype=torch.float64, device=eigvals[0].device)
+    return out
+
+
 class _KronNLL(torch.autograd.Function):
-    """S = kron(K_0..K_M) + tau I;  returns (0.5*log|S| + 0.5*vec(Y)^T S^-1 vec(Y),  A,  g = S^-1 vec(Y)).
+    """S = kron(K_0..K_M) + tau I (+ E);  returns (0.5*log|S| + 0.5*vec(Y)^T S^-1 vec(Y),  A,  g = S^-1 vec(Y)).
     Gradient (closed form, no differentiation through eigh):
       dY = g;  dtau = 0.5*(sum 1/A - sum h^2), h = T1/A;
       dK_k = 0.5 * U_k (diag(c_k) - Q_k) U_k^T,  c_k[j] = sum_{i_k=j} prod_{m!=k} lambda_m / A,
-      Q_k = weighted mode-k Gram matrix of h."""
+      Q_k = weighted mode-k Gram matrix of h.
+    `add` is a number (fused core / reduction kernels) or a tensor E broadcastable to Y's shape, added to A element
+    by element in the eigenbasis exactly as the reference's `A = A + y_var` does (hogp.py:176): the eigensolves, mode
+    products and mode Grams stay on our kernels, the element-wise stage runs as torch device ops, dE = 0.5 (1/A - h^2).
+    With a tensor E the objective is no longer a function of S alone (E lives in the eigenbasis), so the eigenvector
+    derivative does not cancel: dK_k = 0.5 U_k (diag(c_k) - Q_k - R_k) U_k^T with
+      R_k[a,b] = (B_k[a,b] - B_k[b,a]) / (lambda_a - lambda_b),  B_k = mode-k Gram of (E o h) with h,  R_k[a,a] = 0
+    (derived in the docstring's notation from du_a = sum_{b != a} u_b (u_b^T dK u_a) / (lambda_a - lambda_b); it matches
+    the reference's autograd through eigh to 1e-13 on tests/golden/hogp2023_yvar.npz).  Exactly equal eigenvalues
+    contribute 0 where the reference returns NaN; R_k vanishes when E is constant along mode k."""
 
     @staticmethod
     def forward(ctx, Y, tau, add, *Ks):
         dev = Y.device
         Yc = ops._f64c(Y)
         sizes = list(Yc.shape)
+        E = None
+        if isinstance(add, torch.Tensor):
+            if add.numel() > 1:
+                E = ops._f64c(add).broadcast_to(sizes)
+            else:
+                add = float(add)
         launched = _eigh_launch_all(Ks)                   # concurrent per-mode solves, one status read
         _eigh_check([l[2] for l in launched])
         eig = [(l[0], l[1]) for l in launched]
@@ -263,12 +293,20 @@ class _KronNLL(torch.autograd.Function):
         for k, (_, U) in enumerate(eig):
             T1 = _mode_dot_raw(T1, U.contiguous(), k, True)          # x_k U_k^T
         tau_t = ops._f64c(tau.reshape(1))
-        h, A, sums = _kron_core(T1, lam_cat, sizes, tau_t, add)
+        if E is None:
+            h, A, sums = _kron_core(T1, lam_cat, sizes, tau_t, add)
+            A_saved = E_saved = torch.empty(0, dtype=torch.float64, device=dev)
+        else:
+            A = (_lambda_product([e[0] for e in eig], sizes) + tau_t + E).contiguous()
+            h = (T1 / A).contiguous()
+            sums = torch.stack([A.log().sum(), (T1 * h).sum(), (1.0 / A).sum(), (h * h).sum()])
+            A_saved, E_saved = A, E.contiguous()
         g = h
         for k, (_, U) in enumerate(eig):
             g = _mode_dot_raw(g, U.contiguous(), k, False)           # x_k U_k
-        ctx.save_for_backward(h, g, sums, lam_cat, tau_t, *[e[1] for e in eig])
-        ctx.meta = (sizes, float(add), Y.dtype, [K.dtype for K in Ks], tau.shape, tau.dtype)
+        ctx.save_for_backward(h, g, sums, lam_cat, tau_t, A_saved, E_saved, *[e[1] for e in eig])
+        ctx.meta = (sizes, None if E is not None else float(add), Y.dtype, [K.dtype for K in Ks], tau.shape, tau.dtype,
+                    (tuple(add.shape), add.dtype) if E is not None else None)
         val = 0.5 * (sums[0] + sums[1])
         A_o, g_o = A.to(Y.dtype), g.to(Y.dtype)
         flat = []
@@ -279,34 +317,50 @@ class _KronNLL(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, go, *_unused):
-        h, g, sums, lam_cat, tau_t = ctx.saved_tensors[:5]
-        Us = ctx.saved_tensors[5:]
-        sizes, add, ydt, kdts, tau_shape, tau_dt = ctx.meta
+        h, g, sums, lam_cat, tau_t, A, E = ctx.saved_tensors[:7]
+        Us = ctx.saved_tensors[7:]
+        sizes, add, ydt, kdts, tau_shape, tau_dt, e_meta = ctx.meta
         dev = h.device
         go = go.to(torch.float64)
         gY = (g * go).to(ydt) if ctx.needs_input_grad[0] else None
         gtau = None
         if ctx.needs_input_grad[1]:
             gtau = (0.5 * (sums[2] - sums[3]) * go).reshape(tau_shape).to(tau_dt)
+        gE = None
+        if e_meta is not None and ctx.needs_input_grad[2]:
+            gE = (0.5 * go * (1.0 / A - h * h)).sum_to_size(e_meta[0]).to(e_meta[1])
+        lams = list(torch.split(lam_cat, [int(n) for n in sizes])) if e_meta is not None else None
         gKs = []
         for k, U in enumerate(Us):
             if not ctx.needs_input_grad[3 + k]:
                 gKs.append(None)
                 continue
-            c_k = _kron_ck(lam_cat, sizes, k, tau_t, add, dev)                       # sum_{i_k=j} prod_{m!=k} lambda_m / A
-            hk = _kron_scale(h, lam_cat, sizes, k, 0, tau_t, add, dev)               # h o prod_{m!=k} lambda_m
+            if e_meta is None:
+                c_k = _kron_ck(lam_cat, sizes, k, tau_t, add, dev)                   # sum_{i_k=j} prod_{m!=k} lambda_m / A
+                hk = _kron_scale(h, lam_cat, sizes, k, 0, tau_t, add, dev)           # h o prod_{m!=k} lambda_m
+            else:
+                w = _lambda_product(lams, sizes, skip=k)
+                other = [m for m in range(len(sizes)) if m != k]
+                c_k = (w / A).sum(dim=other) if other else (w / A).reshape(-1)
+                hk = (h * w).contiguous()
             Qk = _mode_gram_raw(h, hk, k)
-            Mk = (torch.diag(c_k) - Qk).contiguous()
+            Mk = torch.diag(c_k) - Qk
+            if e_meta is not None:
+                Bk = _mode_gram_raw((E * h).contiguous(), h, k)
+                gap = lams[k].reshape(-1, 1) - lams[k].reshape(1, -1)
+                nz = gap != 0
+                Mk = Mk - torch.where(nz, (Bk - Bk.T) / torch.where(nz, gap, torch.ones_like(gap)), torch.zeros_like(gap))
+            Mk = Mk.contiguous()
             Uc = U.contiguous()
             gK = _mode_dot_raw(_mode_dot_raw(Mk, Uc, 0, False), Uc, 1, False)        # U M U^T
             gKs.append((0.5 * go * gK).to(kdts[k]))
-        return (gY, gtau, None) + tuple(gKs)
+        return (gY, gtau, gE) + tuple(gKs)
 
 
 def kron_nll(Y, Ks, tau, add=0.0):
     """Differentiable Kronecker-GP objective.  Returns (value, A, g, [(lambda_k, U_k)]); value excludes the
-    0.5*nd*log(2 pi) constant."""
-    out = _KronNLL.apply(Y, tau, float(add), *Ks)
+    0.5*nd*log(2 pi) constant.  `add`: a number, or a tensor broadcastable to Y (the reference's tensor-valued y_var)."""
+    out = _KronNLL.apply(Y, tau, add if isinstance(add, torch.Tensor) else float(add), *Ks)
     val, A, g = out[:3]
     eig = [(out[3 + 2 * k], out[4 + 2 * k]) for k in range(len(Ks))]
     return val, A, g, eig

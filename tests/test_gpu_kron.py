@@ -190,6 +190,35 @@ def test_hogp2023_nondefault_params_and_y_gradient():
     assert rel_err(u.cpu(), g['u']) < 1e-8 and rel_err(v.cpu(), g['var']) < 1e-8
 
 
+@pytest.mark.parametrize('tag', ['full', 'bcast'])
+def test_hogp2023_tensor_valued_y_var(tag):
+    """HOGP.compute_loss(x, y, y_var=<tensor>) (`A = A + y_var` element by element, hogp.py:176) against the unmodified
+    reference (golden hogp2023_yvar.npz): loss, dL/dY, dL/dy_var, A, g, noise and kernel-parameter gradients, and the
+    posterior that reuses A.  `full`: one variance per element of A; `bcast`: a per-sample variance broadcast over the grid."""
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    g = load_golden('hogp2023_yvar')
+    h = HOGP({'fidelity_shapes': [torch.Size([6, 5, 3])]}).double()
+    with torch.no_grad():
+        h.noise_box.value.fill_(2.5)
+        for i, k in enumerate(h.kernel_list):
+            k.length_scale.fill_(-1.2 + 0.25 * i)
+            k.scale.fill_(0.1 * (i + 1))
+    h = h.to(DEV)
+    Y = G(g['Y']).requires_grad_(True)
+    yv = G(g[f'{tag}_y_var']).requires_grad_(True)
+    loss = h.compute_loss(G(g['x']), Y, y_var=yv)
+    assert abs(loss.item() - float(g[f'{tag}_loss'])) <= 1e-9 * abs(float(g[f'{tag}_loss']))
+    loss.backward()
+    assert rel_err(Y.grad.cpu(), g[f'{tag}_gY']) < 1e-9 and rel_err(yv.grad.cpu(), g[f'{tag}_g_y_var']) < 1e-9
+    assert rel_err(h.A.cpu(), g[f'{tag}_A']) < 1e-9 and rel_err(h.g.cpu(), g[f'{tag}_g']) < 1e-8
+    assert rel_err(h.noise_box.value.grad.cpu(), g[f'{tag}_g_noise']) < 1e-8
+    for k in range(4):
+        assert _close_or_ref_nan(h.kernel_list[k].length_scale.grad.cpu(), g[f'{tag}_g_ls{k}'])
+        assert _close_or_ref_nan(h.kernel_list[k].scale.grad.cpu(), g[f'{tag}_g_sc{k}'])
+    u, v = h.forward(G(g['xs']))
+    assert rel_err(u.cpu(), g[f'{tag}_u']) < 1e-8 and rel_err(v.cpu(), g[f'{tag}_var']) < 1e-8
+
+
 def test_hogp_hyper_gradient_arbiter():
     """Which side of the 1e-6 disagreement on HOGP kernel-parameter gradients carries the error?  The reference
     differentiates THROUGH torch.linalg.eigh (hogp.py:18-22; backward has 1/(lambda_i - lambda_j) terms, ill-conditioned

@@ -325,3 +325,23 @@ def test_single_fidelity_acquisition_scores_pinned_on_the_reference_module():
     assert pi.dtype == torch.float32 and np.array_equal(pi.numpy(), g['PI_score'])
     pf = O.acq_sf_score('PF', T(g['pf_mean']), T(g['pf_var']), thresholds=list(g['pf_thresholds']))
     assert np.array_equal(pf, g['PF_score'])
+
+
+@pytest.mark.parametrize('tag', ['full', 'bcast'])
+def test_hogp2023_tensor_valued_y_var(tag):
+    """O.hogp_loss with a tensor y_var (`A = A + y_var`, hogp.py:176) against the unmodified HOGP.compute_loss (golden
+    from oracle/gen_golden_hogp_yvar.py): one value per element of A, and a per-sample variance broadcast over the grid."""
+    g = load_golden('hogp2023_yvar')
+    params = [(-1.2 + 0.25 * i, 0.1 * (i + 1)) for i in range(4)]
+    x, Y, xs, ps, Ks = _hogp_from_golden(g, 3, params)
+    Y = Y.clone().requires_grad_(True)
+    yv = P(g[f'{tag}_y_var'])
+    nv = P(2.5)
+    loss, A, gg = O.hogp_loss(Ks, nv.pow(-1), Y, y_var=yv)
+    assert rel_err(loss.detach(), g[f'{tag}_loss']) < 1e-12
+    loss.backward()
+    assert rel_err(Y.grad, g[f'{tag}_gY']) < 1e-10 and rel_err(yv.grad, g[f'{tag}_g_y_var']) < 1e-10
+    assert rel_err(A.detach(), g[f'{tag}_A']) < 1e-10 and rel_err(gg.detach(), g[f'{tag}_g']) < 1e-9
+    assert rel_err(nv.grad, g[f'{tag}_g_noise']) < 1e-9
+    for k in range(4):
+        assert rel_err(ps[k][0].grad, g[f'{tag}_g_ls{k}']) < 1e-7 and rel_err(ps[k][1].grad, g[f'{tag}_g_sc{k}']) < 1e-7
