@@ -22,8 +22,16 @@ print('batched nll', float(out['nll'].sum()))
 B2, n2 = 8, 256
 x2 = torch.rand(B2, n2, d, generator=g).cuda(); y2 = torch.randn(B2, n2, 1, generator=g).cuda()
 out2 = batched_cigp_eval(x2, y2, (torch.rand(B2, d, generator=g) + 0.5).cuda(), torch.ones(B2).cuda(), torch.rand(B2, generator=g).cuda(),
-                         torch.rand(B2, ns, d, generator=g).cuda())
-print('batched f256 nll', float(out2['nll'].sum()))
+                         torch.rand(B2, ns, d, generator=g).cuda(), acq=dict(kind='EI', f_best=0.2, xi=0.01))
+print('batched f256 nll', float(out2['nll'].sum()), 'score', float(out2['score'].sum()))
+# third session of round 2: acquisition kinds of the stand-alone kernel (incl. the single-fidelity UCB / PI)
+from fidelityfusion_b200.MF_BayesianOptimization.Discrete.DMF_acq import acquisition
+for kind in ('UCB', 'EI', 'PI', 'UCB_STD', 'PI_CDF'):
+    mu_ = out2['mean'][..., 0].clone().requires_grad_(True); v_ = out2['var'].clone().requires_grad_(True)
+    s_ = acquisition(mu_, v_, kind, f_best=0.2, beta=1.5, xi=0.01)
+    if kind != 'PI_CDF':
+        s_.sum().backward()
+print('batched acq kinds ok')
 m = cigp(ARDKernel(5), 1.0).cuda()
 xx = torch.rand(200, 5, generator=g).cuda(); yy = torch.randn(200, 24, generator=g).cuda()
 (-m.negative_log_likelihood(xx, yy)).backward()
