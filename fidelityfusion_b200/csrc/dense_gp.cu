@@ -1080,21 +1080,28 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
     }
     return 0;
   };
-  // Experiment (FFGP_SPLIT=1, default off): the two halves of a chunk on TWO streams, so that the ramp-up / drain of the
-  // ~30 dependent launches of one half (~11 us per launch, profiles/r02_gemm_small_k_tiles.txt) is filled by the other
-  // half's CTAs.  Measured on BASELINE config 5: 41.56 ms per sweep against 41.07 ms on one stream
-  // (profiles/r02_c5_experiments.txt) - every GEMM CTA owns a whole SM, so the second chain only ever gets the SMs the
-  // first one has drained, and each half has half as many waves to amortise its own launches over.
+  // Two streams for one chunk (FFGP_SPLIT):
+  //   2 (default)  tail split: only the problems of the last, partial wave of the one-CTA-per-problem launches (nb mod SM
+  //                count) go to the library's second stream, so that their fused 256-block CTAs overlap the first part's next
+  //                product instead of leaving most SMs idle for a whole wave.  512 problems per GPU (BASELINE config 5 on 8
+  //                GPUs) = 3.46 waves of 148: 5.485 -> 5.366 ms per sweep (-2.2 %, same results bit for bit); 4096 problems
+  //                (tail 100): 38.10 vs 38.12 ms, neutral (profiles/r02_c5_experiments.txt).
+  //   1            the two HALVES of a chunk on two streams, so that the ramp-up / drain of the ~30 dependent launches of one
+  //                half is filled by the other half's CTAs: 41.56 ms per sweep against 41.07 on one stream - every GEMM CTA
+  //                owns a whole SM, so the second chain only ever gets the SMs the first one has drained.  Not adopted.
+  //   0            one stream.
   static int split_on = -1;
-  if (split_on < 0) { const char* e = getenv("FFGP_SPLIT"); split_on = (e && atoi(e) == 1) ? 1 : 0; }
+  if (split_on < 0) { const char* e = getenv("FFGP_SPLIT"); split_on = e ? atoi(e) : 2; if (split_on < 0 || split_on > 2) split_on = 2; }
   for (int b0 = 0; b0 < batch; b0 += w.chunk) {
     const int nb = std::min(w.chunk, batch - b0);
     g_persist = nb >= 8;      // same rule as the look-ahead switch: a large batch fills the machine by itself
     int rc;
     AuxStream* aux = nullptr;
-    if (split_on && !reuse_factor && nb >= 4 * num_sms() && debug_stop_after() == 0 && get_aux(&aux) == cudaSuccess) {
+    const int tail = nb % num_sms();
+    if (((split_on == 1 && nb >= 4 * num_sms()) || (split_on == 2 && nb >= 2 * num_sms() && tail >= 8 && tail <= num_sms() * 3 / 4)) &&
+        !reuse_factor && debug_stop_after() == 0 && get_aux(&aux) == cudaSuccess) {
       const int sms = num_sms();
-      const int na = std::min(nb - sms, (nb / 2 + sms - 1) / sms * sms);          // first half, whole waves
+      const int na = split_on == 2 ? nb - tail : std::min(nb - sms, (nb / 2 + sms - 1) / sms * sms);   // whole waves first
       FFGP_CUDA(cudaEventRecord(aux->ev_fork, st));
       FFGP_CUDA(cudaStreamWaitEvent(aux->st_bulk, aux->ev_fork, 0));
       if ((rc = run_chunk(b0, na, w, st)) != 0) return rc;
