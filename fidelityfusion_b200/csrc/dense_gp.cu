@@ -1084,8 +1084,9 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
   //   2 (default)  tail split: only the problems of the last, partial wave of the one-CTA-per-problem launches (nb mod SM
   //                count) go to the library's second stream, so that their fused 256-block CTAs overlap the first part's next
   //                product instead of leaving most SMs idle for a whole wave.  512 problems per GPU (BASELINE config 5 on 8
-  //                GPUs) = 3.46 waves of 148: 5.485 -> 5.366 ms per sweep (-2.2 %, same results bit for bit); 4096 problems
-  //                (tail 100): 38.10 vs 38.12 ms, neutral (profiles/r02_c5_experiments.txt).
+  //                GPUs) = 3.46 waves of 148: 5.485 -> 5.29 ms per sweep (-3.6 %, same results bit for bit); 4096 problems
+  //                (tail 100): 38.10 vs 38.12 ms, neutral; 1024 / 2048 problems (tails 136 / 124: last wave > 3/4 full) are
+  //                not split - every split point measured there is neutral or slower (profiles/r02_c5_experiments.txt).
   //   1            the two HALVES of a chunk on two streams, so that the ramp-up / drain of the ~30 dependent launches of one
   //                half is filled by the other half's CTAs: 41.56 ms per sweep against 41.07 on one stream - every GEMM CTA
   //                owns a whole SM, so the second chain only ever gets the SMs the first one has drained.  Not adopted.
@@ -1101,7 +1102,13 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
     if (((split_on == 1 && nb >= 4 * num_sms()) || (split_on == 2 && nb >= 2 * num_sms() && tail >= 8 && tail <= num_sms() * 3 / 4)) &&
         !reuse_factor && debug_stop_after() == 0 && get_aux(&aux) == cudaSuccess) {
       const int sms = num_sms();
-      const int na = split_on == 2 ? nb - tail : std::min(nb - sms, (nb / 2 + sms - 1) / sms * sms);   // whole waves first
+      // mode 2: whole waves first; below four waves the two parts are made comparable (512 problems: 296 + 216 measured
+      // 5.290 ms, 444 + 68: 5.366, 148 + 364: 5.323, one stream: 5.485), above that only the partial wave moves
+      int na = split_on == 2 ? (nb < 4 * sms ? ((nb / sms) + 1) / 2 * sms : nb - tail)
+                             : std::min(nb - sms, (nb / 2 + sms - 1) / sms * sms);
+      static int na_override = -1;                  // FFGP_SPLIT_NA: size of the first part (experiments)
+      if (na_override < 0) { const char* e = getenv("FFGP_SPLIT_NA"); na_override = e ? atoi(e) : 0; }
+      if (na_override > 0 && na_override < nb) na = na_override;
       FFGP_CUDA(cudaEventRecord(aux->ev_fork, st));
       FFGP_CUDA(cudaStreamWaitEvent(aux->st_bulk, aux->ev_fork, 0));
       if ((rc = run_chunk(b0, na, w, st)) != 0) return rc;
