@@ -8,7 +8,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 n, d, ns = 512, 8, 64
 g = torch.Generator().manual_seed(5)
 x = torch.rand(B, n, d, generator=g, dtype=torch.float64); w = torch.randn(B, d, 1, generator=g, dtype=torch.float64)
-y = torch.sin(3 * x @ w) + 0.05 * torch.randn(B, n, 1, generator=g, dtype=torch.float64)
+y = torch.sin(3 * sum(x[..., k:k + 1] * w[:, k:k + 1, :] for k in range(d))) + 0.05 * torch.randn(B, n, 1, generator=g, dtype=torch.float64)
 ls = torch.exp(torch.rand(B, d, generator=g, dtype=torch.float64) * 2 - 1); sv = torch.ones(B, dtype=torch.float64)
 lb = torch.rand(B, generator=g, dtype=torch.float64) * 3; xs = torch.rand(B, ns, d, generator=g, dtype=torch.float64)
 x, y, ls, sv, lb, xs = (t.cuda() for t in (x, y, ls, sv, lb, xs))
