@@ -93,7 +93,7 @@ class HOGP(torch.nn.Module):
             self.train_y = y
         self.compute_kernel_cache()
         # hogp.py:176 `A = A + y_var`: a number, or a tensor broadcast against A element by element
-        add = y_var if isinstance(y_var, torch.Tensor) and y_var.numel() > 1 else float(y_var)
+        add = y_var if isinstance(y_var, torch.Tensor) and (y_var.numel() > 1 or y_var.requires_grad) else float(y_var)
         val, A, g, eig = tl.kron_nll(self.train_y, self.k_result_cache, self.noise_box.get().pow(-1), add)
         self.eigen_cache = [eigen_pairs(value=lam, vector=U) for lam, U in eig]
         self.A = A

@@ -281,7 +281,7 @@ class _KronNLL(torch.autograd.Function):
         sizes = list(Yc.shape)
         E = None
         if isinstance(add, torch.Tensor):
-            if add.numel() > 1:
+            if add.numel() > 1 or add.requires_grad:      # a one-element tensor that needs its gradient is broadcast too
                 E = ops._f64c(add).broadcast_to(sizes)
             else:
                 add = float(add)

@@ -219,6 +219,40 @@ def test_hogp2023_tensor_valued_y_var(tag):
     assert rel_err(u.cpu(), g[f'{tag}_u']) < 1e-8 and rel_err(v.cpu(), g[f'{tag}_var']) < 1e-8
 
 
+def test_hogp2023_scalar_tensor_y_var_with_gradient():
+    """A ONE-element tensor y_var that requires grad (the reference's `A = A + y_var` is differentiable in it, hogp.py:176):
+    loss, dL/dy_var and dL/dY against the CPU oracle on the same inputs; a plain number takes the fused scalar path and
+    gives the same loss."""
+    from fidelityfusion_b200.MFGP_ver2023May import HOGP
+    g = load_golden('hogp2023_yvar')
+    params = [(-1.2 + 0.25 * i, 0.1 * (i + 1)) for i in range(4)]
+    h = HOGP({'fidelity_shapes': [torch.Size([6, 5, 3])]}).double()
+    with torch.no_grad():
+        h.noise_box.value.fill_(2.5)
+        for i, k in enumerate(h.kernel_list):
+            k.length_scale.fill_(params[i][0])
+            k.scale.fill_(params[i][1])
+    h = h.to(DEV)
+    Y = G(g['Y']).requires_grad_(True)
+    yv = torch.tensor(0.07, dtype=torch.float64, device=DEV, requires_grad=True)
+    loss = h.compute_loss(G(g['x']), Y, y_var=yv)
+    loss.backward()
+    # oracle
+    x, Yc = torch.as_tensor(g['x']), torch.as_tensor(g['Y']).clone().requires_grad_(True)
+    grids = [torch.arange(s, dtype=torch.float64).reshape(-1, 1) for s in (6, 5, 3)]
+    T = lambda v: torch.tensor(v, dtype=torch.float64)
+    Ks = [O.se_kernel(x, x, T(params[0][0]), T(params[0][1]), False)]
+    for k, gr in enumerate(grids):
+        Ks.append(O.se_kernel(gr, gr, T(params[k + 1][0]), T(params[k + 1][1]), False))
+    yvc = torch.tensor(0.07, dtype=torch.float64, requires_grad=True)
+    lo, _, _ = O.hogp_loss(Ks, T(2.5).pow(-1), Yc, y_var=yvc)
+    lo.backward()
+    assert abs(loss.item() - lo.item()) <= 1e-9 * abs(lo.item())
+    assert rel_err(yv.grad.cpu(), yvc.grad) < 1e-9 and rel_err(Y.grad.cpu(), Yc.grad) < 1e-9
+    loss_num = h.compute_loss(G(g['x']), G(g['Y']), y_var=0.07)
+    assert abs(loss_num.item() - lo.item()) <= 1e-9 * abs(lo.item())
+
+
 def test_hogp_hyper_gradient_arbiter():
     """Which side of the 1e-6 disagreement on HOGP kernel-parameter gradients carries the error?  The reference
     differentiates THROUGH torch.linalg.eigh (hogp.py:18-22; backward has 1/(lambda_i - lambda_j) terms, ill-conditioned

@@ -148,3 +148,34 @@ def test_fused_adam_table_cache_is_bounded_and_capture_safe_api():
         FusedAdam([p], lr=-1.0)
     with pytest.raises(ValueError):
         FusedAdam([p], betas=(1.0, 0.9))
+
+
+def test_acquisition_mirrors_fail_loudly_without_cuda_and_keep_the_reference_surface():
+    """Bayesian_optimization.acq (reference acq.py:118-294): constructor defaults and forward arities of the reference, no
+    CPU fallback for the scores, and the packed-row layout of a batched sweep with the score block."""
+    import inspect
+    from fidelityfusion_b200 import _lib
+    from fidelityfusion_b200.Bayesian_optimization import acq as A
+    from fidelityfusion_b200.batched import result_layout, result_shapes, empty_result, unpack_results
+    mu, var = torch.zeros(5, 1, dtype=torch.float64), torch.ones(5, 1, dtype=torch.float64)
+    ucb, ei, pi, kg = A.UCB(lambda X: mu, lambda X: var), A.EI(lambda X: mu, lambda X: var), A.PI(lambda X: mu, lambda X: var), \
+        A.KG(lambda X: mu, lambda X: var)
+    assert (ucb.kappa, ei.xi, pi.sita, kg.num_fantasies) == (2.0, 0.01, 0.01, 10)
+    assert [len(inspect.signature(f.forward).parameters) for f in (ucb, ei, pi, kg)] == [1, 2, 2, 2]     # acq.py:31-42 dispatches on this
+    assert list(inspect.signature(A.optimize_acqf).parameters) == ['acq', 'raw_samples', 'bounds', 'f_best', 'num_restarts', 'options']
+    assert list(inspect.signature(A.find_next_batch).parameters) == ['acq', 'bounds', 'batch_size', 'n_samples', 'f_best']
+    for call in (lambda: ucb.forward(None), lambda: ei.forward(None, 0.0), lambda: pi.forward(None, 0.0)):
+        with pytest.raises(_lib.FFGPError):
+            call()
+    # KG and PF are torch expressions of the caller's posterior (Monte-Carlo fantasies / a product of normal cdfs)
+    assert tuple(kg.forward(None, 0.0).shape) == (1,)
+    pf = A.PF(lambda X: torch.zeros(4, 2, dtype=torch.float64), lambda X: torch.ones(4, 2, dtype=torch.float64), [0.0, 0.0])
+    assert torch.allclose(pf.forward(torch.zeros(4, 3)), torch.full((4,), 0.25, dtype=torch.float64))
+    # packed row with the score block: [nll | grads | mean | var | score | info]
+    keys, widths = result_layout(3, 1, 4, True, False, True)
+    assert keys == ['nll', 'g_length_scales', 'g_signal_variance', 'g_log_beta', 'mean', 'var', 'score', 'info']
+    assert widths == [1, 3, 1, 1, 4, 4, 4, 1]
+    buf = torch.arange(2 * sum(widths), dtype=torch.float64).reshape(2, -1)
+    out = unpack_results(buf, result_shapes(3, 1, 4), keys)
+    assert tuple(out['score'].shape) == (2, 4) and float(out['score'][0, 0]) == 14.0 and float(out['info'][1]) == 2 * 19 - 1
+    assert tuple(empty_result(3, 1, 4, True, True, 'cpu', True)['score'].shape) == (0, 4)
