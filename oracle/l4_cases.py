@@ -297,6 +297,43 @@ def case_cigar2023(dev, steps=10, lr=0.01):
     return out
 
 
+def case_bo_cigp_acq(dev, steps=30, lr=1e-2, n=48, n_cand=64):
+    """One single-fidelity Bayesian-optimisation step built from the reference's own pieces (SURVEY 8f rank 2 callers):
+    Bayesian_optimization/cigp.py CIGP_withMean - unmodified: ARDKernel + gp_computation_pack.Gaussian_log_likelihood
+    (log_likelihood, :86-91) / conditional_Gaussian (forward, :61-84), input / output normalisation in torch - trained with
+    Adam, then Bayesian_optimization/acq.py UCB / EI / PI (:118-231) on its posterior at a candidate set, and the arg-max
+    candidate of each score."""
+    from Bayesian_optimization.cigp import CIGP_withMean
+    from Bayesian_optimization import acq as A
+    import GaussianProcess.kernel as kernel
+    g = torch.Generator(device='cpu').manual_seed(31)
+    xtr = (torch.rand(n, 2, generator=g, device='cpu') * 4 - 2).to(dev)
+    ytr = (torch.sin(2 * xtr[:, :1]) * torch.cos(xtr[:, 1:]) + 0.05 * torch.randn(n, 1, generator=g, device='cpu').to(dev))
+    cand = (torch.rand(n_cand, 2, generator=g, device='cpu') * 4 - 2).to(dev)
+    model = CIGP_withMean(2, 1, kernel=kernel.ARDKernel(2), noise_variance=0.5).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    losses = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = -model.log_likelihood(xtr, ytr)
+        losses.append(float(loss.detach().reshape(-1)[0].item()))
+        loss.backward()
+        opt.step()
+    out = {'losses': torch.tensor(losses, dtype=torch.float64)}
+    _params(model, out)
+    with torch.no_grad():
+        mean_f = lambda X: model.forward(xtr, ytr, X)[0]
+        var_f = lambda X: model.forward(xtr, ytr, X)[1]
+        mu, var = model.forward(xtr, ytr, cand)
+        f_best = float(ytr.max())
+        ucb = _quiet(A.UCB(mean_f, var_f, kappa=2.0).forward, cand)
+        ei = _quiet(A.EI(mean_f, var_f, xi=0.01).forward, cand, f_best)
+        pi = _quiet(A.PI(mean_f, var_f, sita=0.01).forward, cand, f_best)
+    out.update(mu=mu, var=var, ucb=ucb, ei=ei, pi=pi.to(torch.float64),
+               next_ucb=cand[torch.argmax(ucb)], next_ei=cand[torch.argmax(ei)])
+    return out
+
+
 CASES = {
     'l4_cigar3_c3': case_cigar3_c3,
     'l4_ar3_nonsubset': case_ar3_nonsubset,
@@ -306,6 +343,7 @@ CASES = {
     'l4_ar2023_c1': case_ar2023_c1,
     'l4_gar2023_c4': case_gar2023_c4,
     'l4_cigar2023': case_cigar2023,
+    'l4_bo_cigp_acq': case_bo_cigp_acq,
 }
 
 

@@ -124,13 +124,15 @@ def test_alias_table_covers_every_operator_module_the_l4_files_import():
 # north-star tolerance (1e-9 relative) on every recorded quantity: per-iteration losses, final parameters, first-step
 # gradients, predictions.  Measured on B200 (profiles/r02_l4_binding_on_b200.txt): dense paths 1e-14, Kronecker paths
 # <= 2.2e-10 after 8 Adam steps although the reference differentiates THROUGH eigh and we use the closed form.
-_LOOSE = {}
+# EI / PI carry the float32-rounded normal cdf / pdf of the reference (acq.py:178, 230): one float32 ulp where erfc and
+# scipy's ndtr round differently
+_LOOSE = {'l4_bo_cigp_acq': {'ei': 2e-7, 'pi': 2e-7}}
 
 
 @needs_ref
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', ['l4_cigar3_c3', 'l4_ar3_nonsubset', 'l4_resgp2_nonsubset', 'l4_nar2_nonsubset',
-                                  'l4_gar2_c4', 'l4_ar2023_c1', 'l4_gar2023_c4', 'l4_cigar2023'])
+                                  'l4_gar2_c4', 'l4_ar2023_c1', 'l4_gar2023_c4', 'l4_cigar2023', 'l4_bo_cigp_acq'])
 def test_unmodified_reference_l4_trains_on_cuda_drop_ins(case):
     """The reference's own train_* / compute_loss / forward on .cuda() models after binding.install(): per-iteration
     losses, final parameters and predictions against the SAME code on the CPU reference (tests/golden/l4_*.npz)."""
@@ -139,6 +141,6 @@ def test_unmodified_reference_l4_trains_on_cuda_drop_ins(case):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     rep = json.loads(r.stdout.strip().splitlines()[-1])['cases'][case]
     assert rep['ffgp_launches'] > 0, 'no libffgp kernel ran: the binding fell through to torch'
-    tol = _LOOSE.get(case, 1e-9)
-    bad = {k: v for k, v in rep['rel_err'].items() if not v < tol}
+    loose = _LOOSE.get(case, {})
+    bad = {k: v for k, v in rep['rel_err'].items() if not v < loose.get(k, 1e-9)}
     assert not bad, f'{case}: {bad}'

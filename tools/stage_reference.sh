@@ -10,7 +10,7 @@ DST="$ROOT/baseline/_ref"
 rm -rf "$DST"
 mkdir -p "$DST/Experiments"
 cd "$SRC"
-for d in FidelityFusion_Models GaussianProcess MFGP_ver2023May MF_BayesianOptimization; do
+for d in FidelityFusion_Models GaussianProcess MFGP_ver2023May MF_BayesianOptimization Bayesian_optimization; do
   find "$d" -name '*.py' | while read -r f; do
     mkdir -p "$DST/$(dirname "$f")"
     cp "$f" "$DST/$f"
