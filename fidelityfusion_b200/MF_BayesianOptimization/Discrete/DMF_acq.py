@@ -10,7 +10,7 @@ from ... import _lib as B
 from ... import ops
 
 PI = 3.1415926
-KINDS = {'UCB': 0, 'EI': 1, 'PI': 2, 'UCB_STD': 3, 'PI_CDF': 4}       # 3 / 4: Bayesian_optimization/acq.py's UCB / PI
+from ...batched import ACQ_KINDS as KINDS           # {'UCB': 0, 'EI': 1, 'PI': 2, 'UCB_STD': 3, 'PI_CDF': 4}
 
 
 class _Acq(torch.autograd.Function):
@@ -143,5 +143,5 @@ def batched_candidate_scores(x, y, length_scales, signal_variance, log_beta, xs,
     from ...batched import batched_cigp_eval
     # the score is written by the epilogue of the sweep (ffgp_batched_pack_acq_f64): no launch of its own
     out = batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs, want_grad=False,
-                            acq=dict(kind=KINDS[kind] if isinstance(kind, str) else kind, f_best=f_best, beta=beta, xi=xi))
+                            acq=dict(kind=kind, f_best=f_best, beta=beta, xi=xi))
     return out['score']

@@ -23,7 +23,10 @@ PI = 3.1415
 EPS = 1e-9
 
 
-ACQ_KINDS = {'UCB_MF': 0, 'EI': 1, 'PI_MF': 2, 'UCB': 3, 'PI': 4}
+# score kinds of ffgp_acquisition_f64 / ffgp_batched_pack_acq_f64 (one vocabulary for the whole package):
+#   'UCB', 'EI', 'PI'      DiscreteAcquisitionFunction.UCB_MF / EI_MF / PI_MF (MF_BayesianOptimization/Discrete/DMF_acq.py:49-128)
+#   'UCB_STD', 'PI_CDF'    UCB / PI of the single-fidelity module (Bayesian_optimization/acq.py:135-231); its EI is 'EI'
+ACQ_KINDS = {'UCB': 0, 'EI': 1, 'PI': 2, 'UCB_STD': 3, 'PI_CDF': 4}
 
 
 def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, want_grad=True, check=True, acq=None):
@@ -39,7 +42,7 @@ def batched_cigp_eval(x, y, length_scales, signal_variance, log_beta, xs=None, w
     asynchronous (sweeps can be enqueued back to back) and returns the LAPACK-style status as out['info'] (fp64 [B],
     0 = ok, k = leading minor k not PD) for the caller to inspect, e.g. once per optimisation step: `check_batch_info`.
 
-    acq = dict(kind='EI' | 'UCB' | 'PI' | 'UCB_MF' | 'PI_MF', f_best=, beta=, xi=, round_f32=True) (needs xs, D = 1) adds
+    acq = dict(kind=<a key of ACQ_KINDS>, f_best=, beta=, xi=, round_f32=True) (needs xs, D = 1) adds
     out['score'] [B,ns]: the acquisition score of every test point, computed in the epilogue that writes the result rows
     (ffgp_batched_pack_acq_f64) - no extra launch, and it travels through sharded_cigp_eval's single all-gather."""
     from . import _lib as B

@@ -86,7 +86,7 @@ def test_candidate_search_and_optimisation_run_on_the_device():
     assert tuple(best.shape) == (16, 1) and float(ucb.forward(best).sum()) >= float(ucb.forward(start).sum()) - 1e-12
 
 
-@pytest.mark.parametrize('kind', ['EI', 'UCB', 'PI', 'UCB_MF', 'PI_MF'])
+@pytest.mark.parametrize('kind', ['EI', 'UCB', 'PI', 'UCB_STD', 'PI_CDF'])
 def test_batched_sweep_writes_the_scores_in_its_epilogue(kind):
     """out['score'] of batched_cigp_eval(acq=...) (ffgp_batched_pack_acq_f64: the score block of the packed result row)
     equals the stand-alone kernel applied to the sweep's own mean / variance (1e-14: the same device function inlined in
