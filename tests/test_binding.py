@@ -136,6 +136,8 @@ _LOOSE = {'l4_bo_cigp_acq': {'ei': 2e-7, 'pi': 2e-7}}
 def test_unmodified_reference_l4_trains_on_cuda_drop_ins(case):
     """The reference's own train_* / compute_loss / forward on .cuda() models after binding.install(): per-iteration
     losses, final parameters and predictions against the SAME code on the CPU reference (tests/golden/l4_*.npz)."""
+    if case == 'l4_bo_cigp_acq' and not os.path.exists(os.path.join(REF, 'Bayesian_optimization', 'cigp.py')):
+        pytest.skip('the staged reference tree predates tools/stage_reference.sh staging Bayesian_optimization/')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'run_l4_on_gpu.py'), '--ref', REF, '--json', case],
                        capture_output=True, text=True, timeout=1800, cwd='/tmp')
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
