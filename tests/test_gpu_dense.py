@@ -387,6 +387,34 @@ def test_batched_ragged_sizes_through_the_fused_blocks_vs_oracle():
             assert rel_err(out['mean'][b].cpu(), om) < TOL and rel_err(out['var'][b].cpu(), oc.diag()) < TOL
 
 
+def test_batched_tail_split_rows_equal_the_unsplit_evaluation():
+    """330 problems = 2.23 waves of the 148 SMs: the default schedule runs the chunk as two parts on two streams (tail
+    split, dense_gp.cu FFGP_SPLIT=2: 148 + 182 problems).  Every result row must equal, bit for bit, the row the same
+    problem gets in a small batch that is not split (batches under 2 waves never are) - for problems of the first part,
+    of the second part, and across the boundary - and the oracle at 1e-9 on a few of them."""
+    gen = torch.Generator().manual_seed(41)
+    B, n, d, ns = 330, 200, 3, 7
+    x = torch.rand(B, n, d, generator=gen)
+    y = torch.sin(3 * x.sum(2, keepdim=True)) + 0.05 * torch.randn(B, n, 1, generator=gen)
+    ls = torch.rand(B, d, generator=gen) + 0.5
+    sv = torch.ones(B)
+    lb = torch.rand(B, generator=gen) * 3
+    xs = torch.rand(B, ns, d, generator=gen)
+    from fidelityfusion_b200.batched import batched_cigp_eval
+    dev = [t.to(DEV) for t in (x, y, ls, sv, lb, xs)]
+    full = batched_cigp_eval(*dev)
+    assert torch.isfinite(full['_packed']).all()
+    for lo, hi in ((0, 120), (100, 200), (210, 330)):
+        part = batched_cigp_eval(*[t[lo:hi] for t in dev])
+        assert torch.equal(part['_packed'], full['_packed'][lo:hi]), (lo, hi)
+    for b in (0, 147, 148, 329):
+        loss, gr = O.cigp_ard_nll_and_grads(x[b], y[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+        m, c = O.cigp_ard_predict(x[b], y[b], xs[b], ls[b], sv[b:b + 1], lb[b:b + 1])
+        assert abs(float(full['nll'][b]) - loss) <= 1e-9 * abs(loss)
+        assert rel_err(full['g_length_scales'][b], gr['length_scales']) < 1e-9
+        assert rel_err(full['mean'][b], m) < 1e-9 and rel_err(full['var'][b], c.diag()) < 1e-9
+
+
 def test_not_positive_definite_raises_linalg_error():
     from fidelityfusion_b200 import ops
     y = torch.randn(40, 1, device=DEV)
