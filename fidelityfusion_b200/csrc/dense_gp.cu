@@ -914,7 +914,7 @@ int ffgp_dense_fit_f64(const double* x, const double* y, const double* xs, const
   if (amp && (!x || !inv_ls)) return fail(-1, "ffgp_dense_fit_f64: kernel term needs x and inv_ls");
   if (!amp && !sigma_add) return fail(-1, "ffgp_dense_fit_f64: neither a kernel nor a covariance was given");
   if (n <= 0 || D <= 0 || batch <= 0 || d < 0 || ns < 0) return fail(-2, "ffgp_dense_fit_f64: bad size");
-  if (amp && d > GRAD_DMAX && want_grad) return fail(-2, "ffgp_dense_fit_f64: d > 64 not supported with want_grad");
+  if (amp && d > GRAD_DMAX && want_grad) return fail(-2, "ffgp_dense_fit_f64: d > 128 not supported with want_grad");
   if (want_grad && amp && (!g_inv_ls || !g_amp)) return fail(-1, "ffgp_dense_fit_f64: gradient outputs missing");
   if (want_pred) {
     if (ns <= 0) return fail(-2, "ffgp_dense_fit_f64: ns must be positive when predictions are requested");

@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(256) nll_reduce_kernel(const double* __restric
 // src holds S (src_is_G = 0: G formed here from alpha, D <= 8) or G itself (src_is_G = 1).
 // ------------------------------------------------------------------------------------------
 constexpr int GRAD_T = 64;
-constexpr int GRAD_DMAX = 64;   // input dims held in shared memory per tile
+constexpr int GRAD_DMAX = 128;  // input dims held in shared memory per tile (gen-2023 NAR feeds [x, y_low]: d = 2 + 64 at the C1 size)
 
 struct GradParams {
   const double* src; int ld; long long ssrc;

@@ -297,6 +297,26 @@ def case_cigar2023(dev, steps=10, lr=0.01):
     return out
 
 
+def case_family2023(dev, steps=10, lr=0.01):
+    """The other gen-2023 multi-fidelity callers on the C1 data (2 fidelities, N = 100, d = 2, D = 64): ResGP
+    (ResGP.py:200-245 compute_loss, :145-198 forward), NAR (NAR_NonlinearAR.py:188-233, :133-186: the high-fidelity CIGP's
+    input is [x, y_low]) and CAR (CAR_ContinuAR.py:189-233, :134-187: FIDES + Kernel_res on the residual) - compute_loss,
+    first-step gradients, 10 Adam steps, forward on the 100 held-out points."""
+    import MFGP_ver2023May as G23
+    x, xe, y0, y1 = (t.to(dev) for t in data_c1())
+    out = {}
+    for name in ('ResGP', 'NAR', 'CAR'):
+        torch.manual_seed(7)                                   # Kernel_res reseeds the global generator itself (App. A-13)
+        m = getattr(G23, name)({'fidelity_shapes': [(64,), (64,)]}).double().to(dev)
+        losses, g0 = _quiet(_adam_loop, m, lambda: m.compute_loss(x, [y0, y1]), steps, lr)
+        with torch.no_grad():
+            u, v = _quiet(m, xe)
+        out.update({f'{name}_losses': losses, f'{name}_u': u, f'{name}_var': v})
+        out.update({f'{name}_g0_' + k.replace('.', '_'): t for k, t in g0.items()})
+        _params(m, out, prefix=f'{name}_p_')
+    return out
+
+
 def case_bo_cigp_acq(dev, steps=30, lr=1e-2, n=48, n_cand=64):
     """One single-fidelity Bayesian-optimisation step built from the reference's own pieces (SURVEY 8f rank 2 callers):
     Bayesian_optimization/cigp.py CIGP_withMean - unmodified: ARDKernel + gp_computation_pack.Gaussian_log_likelihood
@@ -344,6 +364,7 @@ CASES = {
     'l4_gar2023_c4': case_gar2023_c4,
     'l4_cigar2023': case_cigar2023,
     'l4_bo_cigp_acq': case_bo_cigp_acq,
+    'l4_family2023': case_family2023,
 }
 
 

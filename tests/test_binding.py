@@ -132,7 +132,7 @@ _LOOSE = {'l4_bo_cigp_acq': {'ei': 2e-7, 'pi': 2e-7}}
 @needs_ref
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', ['l4_cigar3_c3', 'l4_ar3_nonsubset', 'l4_resgp2_nonsubset', 'l4_nar2_nonsubset',
-                                  'l4_gar2_c4', 'l4_ar2023_c1', 'l4_gar2023_c4', 'l4_cigar2023', 'l4_bo_cigp_acq'])
+                                  'l4_gar2_c4', 'l4_ar2023_c1', 'l4_gar2023_c4', 'l4_cigar2023', 'l4_bo_cigp_acq', 'l4_family2023'])
 def test_unmodified_reference_l4_trains_on_cuda_drop_ins(case):
     """The reference's own train_* / compute_loss / forward on .cuda() models after binding.install(): per-iteration
     losses, final parameters and predictions against the SAME code on the CPU reference (tests/golden/l4_*.npz)."""
